@@ -1,0 +1,191 @@
+/*
+ * vorta_b200.h — C ABI of the B200-native routed sparse attention path.
+ *
+ * This is the drop-in boundary for the hot path of wenhao728/VORTA (reference citations are relative to the
+ * reference tree).  The reference has no native code: every function below replaces a chain of PyTorch library
+ * calls made by the reference's attention processors.  Only plain pointers, sizes and a cudaStream_t cross the
+ * boundary; the caller owns every buffer; the only hidden state is the opaque vb_plan.
+ *
+ * All device tensors are bf16 unless stated.  Attention tensors are addressed with explicit element strides
+ * (batch, head, token); the channel stride is 1 and head_dim is 128.  That covers both the reference's
+ * (B, H, S, D) view and the (B, S, H, D) memory it is a transpose of (vorta/attention/wan.py:91-94), so no copy
+ * is needed on either side of the call.
+ *
+ * Return value of every int function: VB_OK or a negative VB_ERR_* code; vb_last_error() gives the message of
+ * the last failure on the calling thread.  The Python host maps VB_ERR_INVALID to ValueError (the reference's
+ * _check_input, wan.py:181-193) and the others to RuntimeError.
+ */
+#ifndef VORTA_B200_H_
+#define VORTA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_OK 0
+#define VB_ERR_INVALID (-1)     /* bad shapes / arguments (reference: ValueError) */
+#define VB_ERR_CUDA (-2)        /* CUDA runtime or driver failure */
+#define VB_ERR_UNSUPPORTED (-3) /* valid request this build does not implement */
+
+/* branch ids == the reference's expert order (wan.py:352-354): 0 full, 1 coreset ("lowres"), 2 sliding tile */
+#define VB_BRANCH_FULL 0
+#define VB_BRANCH_CORESET 1
+#define VB_BRANCH_SLIDING 2
+#define VB_BRANCH_SKIP (-1)
+
+#define VB_DTYPE_F32 0
+#define VB_DTYPE_BF16 1
+
+typedef void* vb_stream_t; /* cudaStream_t */
+typedef struct vb_plan vb_plan;
+
+const char* vb_last_error(void);
+int vb_version(void);
+/* 0 when the current device is sm_100 (B200); VB_ERR_UNSUPPORTED otherwise. The product has no other path. */
+int vb_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Plan: geometry-only state shared by all layers and steps.
+ *   replaces get_group_info            (vorta/attention/coreset_select.py:15-60)
+ *            create_sliding_tile_attn_mask_func + create_block_mask (vorta/attention/sliding_attn_flex.py:72-134)
+ *            tile_layout / untile_layout index math (vorta/attention/tile.py:7-78)
+ *            _check_input              (vorta/attention/wan.py:168-193, hunyuan.py:247-272)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t latent[3];        /* (T, H, W) token grid */
+  int32_t tile[3];          /* sliding-tile tile size */
+  int32_t window[3];        /* sliding-tile window, in tiles */
+  int32_t lowres_window[3]; /* coreset group window */
+  int32_t n_unpooled;       /* margins kept per group = int(g * (1 - reduction_rate)) - 1, computed by the host */
+  int32_t text_len;         /* text tokens appended after the video tokens (HunyuanVideo); 0 for Wan */
+  int32_t text_valid;       /* un-padded text tokens, <= text_len */
+} vb_plan_desc;
+
+int vb_plan_create(vb_plan** plan, const vb_plan_desc* desc);
+void vb_plan_destroy(vb_plan* plan);
+/* Change the un-padded text length (HunyuanVideo: per prompt, pipeline_hunyuan.py:380-392) without rebuilding. */
+int vb_plan_set_text_valid(vb_plan* plan, int32_t text_valid);
+
+enum {
+  VB_PLAN_SEQ_LEN = 0,        /* S = T*H*W */
+  VB_PLAN_NUM_GROUPS = 1,     /* G */
+  VB_PLAN_GROUP_SIZE = 2,     /* g */
+  VB_PLAN_CORESET_LEN = 3,    /* S_c = G * (1 + n_unpooled) */
+  VB_PLAN_NUM_TILES = 4,
+  VB_PLAN_TILE_TOKENS = 5,
+  VB_PLAN_NUM_POOLED = 6,     /* dropped margins per group = g - 1 - n_unpooled */
+  VB_PLAN_KEYS_PER_QUERY = 7, /* video keys each video query sees in the sliding branch */
+  VB_PLAN_SLIDING_PAIRS = 8,  /* CTAs per head, sliding branch */
+  VB_PLAN_SLIDING_RUNS = 9    /* entries in the sliding run table */
+};
+int vb_plan_query(const vb_plan* plan, int what, int64_t* value);
+
+enum {
+  VB_EXPORT_CENTER_INDICES = 0, /* int64 (G)        == LowresGroupInfo.center_indices[:, 0] */
+  VB_EXPORT_MARGIN_INDICES = 1, /* int64 (G, g-1)   == LowresGroupInfo.margin_indices */
+  VB_EXPORT_TILE_MAP = 2,       /* int32 (S)  tile-major position -> raster token (tile.py:26-29) */
+  VB_EXPORT_TILE_WINDOW = 3,    /* int32 (num_tiles, 6) lo/hi tile coordinate of each query tile's window */
+  VB_EXPORT_SLIDING_RUNS = 4    /* int32 (runs, 2) start/len in tile-major order */
+};
+/* Copies a host-side table for parity tests; *bytes is in: capacity, out: size. */
+int vb_plan_export(const vb_plan* plan, int what, void* dst, int64_t* bytes);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Router head.  replaces Router.forward (vorta/patch/router.py:33-43) and the top-1 + threshold of
+ * _get_routed_qkv (vorta/attention/wan.py:396-400).  fp32 arithmetic.  n_layers routers at once: weights are
+ * addressed as w + l*w_layer_stride (elements), so one stacked buffer serves a whole denoise step.
+ *   temb   (B, E)           temb_dtype
+ *   w      (L, 3H, E), bias (L, 3H)   w_dtype
+ *   scores (L, B, H, 3) fp32  out
+ *   branch (L, H) int32 out: argmax_e scores[l, 0, h, e]; set to 0 when that score < tau (NaN tau: no threshold)
+ * ---------------------------------------------------------------------------------------------------- */
+int vb_router_forward(const void* temb, int temb_dtype, const void* w, const void* bias, int w_dtype,
+                      int64_t w_layer_stride, int64_t bias_layer_stride, int32_t n_layers, int32_t batch,
+                      int32_t embed_dim, int32_t heads, float tau, float* scores, int32_t* branch,
+                      vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Coreset selection.  replaces the similarity / argsort part of pool_sequence_by_similarity
+ * (vorta/attention/coreset_select.py:91-113).  Dot products and norms accumulate in fp64.
+ *   x (B, H, S[+text], 128) bf16 with element strides; only the first S tokens are read
+ *   unpooled_argsort (B, H, G, n_unpooled) int64, pooled_argsort (B, H, G, g-1-n_unpooled) int64:
+ *        positions inside the group's margin list, ascending similarity (ties: lower position first)
+ *   kept_tok    (B, H, S_c) int32: raster token of every pooled-sequence row ([centres | kept margins])
+ *   dropped_tok (B, H, G, g-1-n_unpooled) int32: raster tokens that receive their centre's output
+ * Any output pointer may be NULL.
+ * ---------------------------------------------------------------------------------------------------- */
+int vb_coreset_select(const vb_plan* plan, const void* x, int64_t stride_b, int64_t stride_h, int64_t stride_s,
+                      int32_t batch, int32_t heads, int64_t* unpooled_argsort, int64_t* pooled_argsort,
+                      int32_t* kept_tok, int32_t* dropped_tok, vb_stream_t stream);
+
+/* Row gather: dst[b, h, i, :] = src[b, h, map[b, h, i], :] for i < n_rows (128 bf16 per row, 16-byte vectors).
+ * replaces the index/gather/cat of pool_sequence_by_similarity (coreset_select.py:91-93,118-123) and
+ * tile_layout (tile.py:7-41).  map strides of 0 share one map across heads / batches. */
+int vb_gather_rows(const void* src, int64_t src_stride_b, int64_t src_stride_h, int64_t src_stride_s, void* dst,
+                   int64_t dst_stride_b, int64_t dst_stride_h, int64_t dst_stride_s, const int32_t* map,
+                   int64_t map_stride_b, int64_t map_stride_h, int32_t batch, int32_t heads, int32_t n_rows,
+                   vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Routed attention for one self-attention layer.
+ *   replaces WanAttnProcessorTripleEval / TripleTrain branches + combine (vorta/attention/wan.py:243-300,
+ *   388-438) and the HunyuanVideo equivalents (hunyuan.py:136-189, 410-513, 612-661), i.e. SDPA,
+ *   flex_attention with the sliding-tile BlockMask, pool / unpool, head gather / scatter and the blend.
+ *
+ *   q, k, v, out: (B, H, S + text_len, 128) bf16 addressed by element strides (batch, head, token)
+ *   branch[H]  : VB_BRANCH_* per head (top-1 mode), ignored in blend mode
+ *   weights    : NULL for top-1 mode (Eval processor); (B, H, 3) fp32 routing scores for blend mode (Train
+ *                processor: every branch on every head, out = sum_e w[b,h,e] * O_e)
+ *   flags      : VB_ATTN_* bits
+ *   workspace  : device scratch of at least vb_attn_workspace_bytes(...) bytes
+ * Text tokens (HunyuanVideo) sit after the video tokens; rows of padded text queries are written as zero.
+ * ---------------------------------------------------------------------------------------------------- */
+#define VB_ATTN_CORESET_KV_FROM_K 1u /* HunyuanVideo: K and V pooled with K's own matching (hunyuan.py:433-438) */
+
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int64_t q_stride[3]; /* batch, head, token (elements) */
+  int64_t k_stride[3];
+  int64_t v_stride[3];
+  int64_t out_stride[3];
+  int32_t batch;
+  int32_t heads;
+  const int32_t* branch; /* host pointer, heads entries */
+  const float* weights;  /* host pointer, batch*heads*3 entries, or NULL */
+  uint32_t flags;
+  void* workspace;
+  int64_t workspace_bytes;
+  float* debug; /* bring-up only; NULL in production */
+} vb_attn_args;
+
+int64_t vb_attn_workspace_bytes(const vb_plan* plan, int32_t batch, int32_t heads);
+int vb_attn_fwd(vb_plan* plan, const vb_attn_args* args, vb_stream_t stream);
+
+/* Counters for bench.py: number of kernels this library launched on the calling thread since the last reset,
+ * and the algorithmic attention FLOPs (BASELINE.md section 3 formulas) they covered. */
+void vb_stats_reset(void);
+int64_t vb_stats_launches(void);
+double vb_stats_attn_flops(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Ulysses sequence parallelism helpers (vorta/ulysses/utils.py:15-93).  The exchange itself is an NCCL
+ * all-to-all issued by the host through torch.distributed; these kernels produce / consume its buffers.
+ *   pack  : x (S_loc, H, 128) token-major -> send (P, S_loc, H/P, 128), chunk p = heads [p*H/P, (p+1)*H/P)
+ *   unpack: recv (P, S_loc, H/P, 128)     -> y (S_loc, H, 128)
+ * The receive buffer of the "in" direction, (P*S_loc, H/P, 128), and the send buffer of the "out" direction are
+ * consumed / produced by vb_attn_fwd directly through its strides, so each direction needs one pass only.
+ * ---------------------------------------------------------------------------------------------------- */
+int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t heads, int32_t world, int32_t n_tensors,
+                          int64_t x_tensor_stride, int64_t send_tensor_stride, vb_stream_t stream);
+int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
+                            vb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VORTA_B200_H_ */

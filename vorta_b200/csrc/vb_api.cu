@@ -1,0 +1,733 @@
+// vb_api.cu — the C ABI (include/vorta_b200.h): plan construction (closed-form schedules, no mask tensors),
+// per-layer orchestration of the three branches, and thin wrappers over the kernels.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "vb_common.cuh"
+
+namespace vb {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static thread_local int64_t g_launches = 0;
+static thread_local double g_flops = 0.0;
+
+// ---- kernels implemented in the other translation units -----------------------------------------
+int launch_coreset_select(const SelectParams& p, cudaStream_t stream);
+int launch_gather_rows(const GatherParams& p, cudaStream_t stream);
+int launch_zero_rows(__nv_bfloat16* out, int64_t sb, int64_t sh, int64_t ss, int batch, int heads, int row0,
+                     int n_rows, cudaStream_t stream);
+int launch_router(const void* temb, int temb_dtype, const void* w, const void* bias, int w_dtype,
+                  int64_t w_layer_stride, int64_t bias_layer_stride, int n_layers, int batch, int embed_dim,
+                  int heads, float tau, float* scores, int32_t* branch, cudaStream_t stream);
+int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
+                           int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream);
+int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
+                        int64_t stride_b, int64_t stride_h, int64_t stride_s);
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
+                int n_pairs, int n_heads, int batch, cudaStream_t stream);
+
+// ---- schedule tables ----------------------------------------------------------------------------
+struct Schedule {
+  std::vector<QPair> pairs;
+  std::vector<KvRun> runs;
+  QPair* d_pairs = nullptr;
+  KvRun* d_runs = nullptr;
+  double flops_per_head = 0.0;   // 4 * D * sum_q keys(q)
+
+  void add_query_range(int row0, int n_rows, int run_begin, int run_count, int64_t keys) {
+    // split [row0, row0+n_rows) into 128-row tiles, two per CTA
+    for (int off = 0; off < n_rows; off += 2 * kBlockM) {
+      QPair qp;
+      memset(&qp, 0, sizeof(qp));
+      qp.run_begin = run_begin;
+      qp.run_count = run_count;
+      qp.q_row0[0] = row0 + off;
+      qp.q_rows[0] = std::min(kBlockM, n_rows - off);
+      qp.nq = 1;
+      if (off + kBlockM < n_rows) {
+        qp.q_row0[1] = row0 + off + kBlockM;
+        qp.q_rows[1] = std::min(kBlockM, n_rows - off - kBlockM);
+        qp.nq = 2;
+      }
+      pairs.push_back(qp);
+    }
+    flops_per_head += 4.0 * kHeadDim * static_cast<double>(n_rows) * static_cast<double>(keys);
+  }
+  int upload() {
+    release();
+    if (!pairs.empty()) {
+      VB_CUDA_OK(cudaMalloc(&d_pairs, pairs.size() * sizeof(QPair)));
+      VB_CUDA_OK(cudaMemcpy(d_pairs, pairs.data(), pairs.size() * sizeof(QPair), cudaMemcpyHostToDevice));
+    }
+    if (!runs.empty()) {
+      VB_CUDA_OK(cudaMalloc(&d_runs, runs.size() * sizeof(KvRun)));
+      VB_CUDA_OK(cudaMemcpy(d_runs, runs.data(), runs.size() * sizeof(KvRun), cudaMemcpyHostToDevice));
+    }
+    return VB_OK;
+  }
+  void release() {
+    if (d_pairs) cudaFree(d_pairs);
+    if (d_runs) cudaFree(d_runs);
+    d_pairs = nullptr;
+    d_runs = nullptr;
+  }
+  void clear() {
+    pairs.clear();
+    runs.clear();
+    flops_per_head = 0.0;
+  }
+};
+
+}  // namespace vb
+
+using namespace vb;
+
+struct vb_plan {
+  vb_plan_desc d;
+  int S = 0, G = 0, g = 0, n_u = 0, n_p = 0, S_c = 0;
+  int nt[3] = {0, 0, 0}, n_tiles = 0, tile_tokens = 0;
+  int64_t keys_per_query = 0;
+  bool has_device = false;
+  // host tables
+  std::vector<int64_t> center, margin;        // (G), (G, g-1)
+  std::vector<int32_t> tile_map;              // (S + text_len): tile-major position -> raster token
+  std::vector<int32_t> tile_window;           // (n_tiles, 6)
+  Schedule full, coreset, sliding;
+  // device tables
+  int32_t* d_center_tok = nullptr;
+  int32_t* d_margin_tok = nullptr;
+  int32_t* d_tile_map = nullptr;
+};
+
+static void window_range(int q, int n, int w, int& lo, int& hi) {
+  // reference: sliding_attn_flex.py:118-127; torch.clamp(min > max) returns max
+  const int half = w / 2;
+  const int cmin = half, cmax = (n - 1) - half;
+  int c = q;
+  if (cmin > cmax) c = cmax;
+  else c = std::min(std::max(q, cmin), cmax);
+  lo = std::max(0, c - half);
+  hi = std::min(n - 1, c + half);
+}
+
+static int build_text_dependent(vb_plan* pl) {
+  const vb_plan_desc& d = pl->d;
+  const int S = pl->S, tv = d.text_valid;
+  // ---- full: every query sees [0, S + text_valid) (wan.py:142-144; hunyuan.py:169-176)
+  pl->full.clear();
+  pl->full.runs.push_back({0, S + tv});
+  pl->full.add_query_range(0, S + tv, 0, 1, S + tv);
+  // ---- coreset: same over the pooled sequence [centres | kept margins | text] (hunyuan.py:440-448)
+  pl->coreset.clear();
+  pl->coreset.runs.push_back({0, pl->S_c + tv});
+  pl->coreset.add_query_range(0, pl->S_c + tv, 0, 1, pl->S_c + tv);
+  // ---- sliding tile, tile-major order (sliding_attn_flex.py:93-127)
+  pl->sliding.clear();
+  pl->tile_window.assign(static_cast<size_t>(pl->n_tiles) * 6, 0);
+  const int tau = pl->tile_tokens;
+  for (int a = 0; a < pl->nt[0]; ++a)
+    for (int b = 0; b < pl->nt[1]; ++b)
+      for (int c = 0; c < pl->nt[2]; ++c) {
+        int lo[3], hi[3];
+        window_range(a, pl->nt[0], d.window[0], lo[0], hi[0]);
+        window_range(b, pl->nt[1], d.window[1], lo[1], hi[1]);
+        window_range(c, pl->nt[2], d.window[2], lo[2], hi[2]);
+        const int tile_id = (a * pl->nt[1] + b) * pl->nt[2] + c;
+        for (int i = 0; i < 3; ++i) {
+          pl->tile_window[tile_id * 6 + i] = lo[i];
+          pl->tile_window[tile_id * 6 + 3 + i] = hi[i];
+        }
+        const int run_begin = static_cast<int>(pl->sliding.runs.size());
+        int64_t keys = 0;
+        for (int x = lo[0]; x <= hi[0]; ++x)
+          for (int y = lo[1]; y <= hi[1]; ++y) {
+            KvRun r;
+            r.start = ((x * pl->nt[1] + y) * pl->nt[2] + lo[2]) * tau;
+            r.len = (hi[2] - lo[2] + 1) * tau;
+            keys += r.len;
+            if (static_cast<int>(pl->sliding.runs.size()) > run_begin &&
+                pl->sliding.runs.back().start + pl->sliding.runs.back().len == r.start) {
+              pl->sliding.runs.back().len += r.len;   // contiguous in tile-major order: merge
+            } else {
+              pl->sliding.runs.push_back(r);
+            }
+          }
+        if (tv > 0) {   // video queries see the valid text keys (:112)
+          pl->sliding.runs.push_back({S, tv});
+          keys += tv;
+        }
+        const int run_count = static_cast<int>(pl->sliding.runs.size()) - run_begin;
+        VB_REQUIRE(run_count <= 32, VB_ERR_UNSUPPORTED, "sliding window needs %d key runs per tile (max 32)",
+                   run_count);
+        pl->sliding.add_query_range(tile_id * tau, tau, run_begin, run_count, keys);
+        if (tile_id == 0) pl->keys_per_query = keys - tv;
+      }
+  if (tv > 0) {   // valid text queries see every non-pad key (:108)
+    const int run_begin = static_cast<int>(pl->sliding.runs.size());
+    pl->sliding.runs.push_back({0, S + tv});
+    pl->sliding.add_query_range(S, tv, run_begin, 1, S + tv);
+  }
+  if (pl->has_device) {
+    int rc;
+    if ((rc = pl->full.upload()) != VB_OK) return rc;
+    if ((rc = pl->coreset.upload()) != VB_OK) return rc;
+    if ((rc = pl->sliding.upload()) != VB_OK) return rc;
+  }
+  return VB_OK;
+}
+
+extern "C" {
+
+const char* vb_last_error(void) { return get_error(); }
+int vb_version(void) { return 100; }
+
+int vb_device_check(void) {
+  int dev = 0, major = 0, minor = 0, count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: vorta_b200 has no CPU path");
+    return VB_ERR_UNSUPPORTED;
+  }
+  VB_CUDA_OK(cudaGetDevice(&dev));
+  VB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  VB_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  VB_REQUIRE(major == 10, VB_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", major,
+             minor);
+  return VB_OK;
+}
+
+int vb_plan_create(vb_plan** out, const vb_plan_desc* desc) {
+  VB_REQUIRE(out != nullptr && desc != nullptr, VB_ERR_INVALID, "null argument");
+  const vb_plan_desc& d = *desc;
+  for (int i = 0; i < 3; ++i) {
+    VB_REQUIRE(d.latent[i] > 0 && d.tile[i] > 0 && d.window[i] > 0 && d.lowres_window[i] > 0, VB_ERR_INVALID,
+               "latent / tile / window sizes must be positive");
+    // reference: wan.py:186-189
+    VB_REQUIRE(d.latent[i] % d.tile[i] == 0, VB_ERR_INVALID,
+               "Tile size (%d, %d, %d) (dim=%d) does not divide latent shape (%d, %d, %d) (dim=%d).", d.tile[0],
+               d.tile[1], d.tile[2], d.tile[i], d.latent[0], d.latent[1], d.latent[2], d.latent[i]);
+  }
+  vb_plan* pl = new vb_plan();
+  pl->d = d;
+  pl->S = d.latent[0] * d.latent[1] * d.latent[2];
+  const int fg = d.latent[0] / d.lowres_window[0], hg = d.latent[1] / d.lowres_window[1],
+            wg = d.latent[2] / d.lowres_window[2];
+  pl->G = fg * hg * wg;
+  pl->g = d.lowres_window[0] * d.lowres_window[1] * d.lowres_window[2];
+  pl->n_u = d.n_unpooled;
+  pl->n_p = pl->g - 1 - pl->n_u;
+  pl->S_c = pl->G * (1 + pl->n_u);
+  auto fail = [&](int code) {
+    delete pl;
+    return code;
+  };
+  // reference: wan.py:191-193 (S == G * g)
+  if (pl->S != pl->G * pl->g) {
+    set_error("Input sequence length %d does not match low-res info %dx%d.", pl->S, pl->G, pl->g);
+    return fail(VB_ERR_INVALID);
+  }
+  if (pl->n_u < 0 || pl->n_p < 0) {
+    set_error("n_unpooled %d out of range for group size %d", pl->n_u, pl->g);
+    return fail(VB_ERR_INVALID);
+  }
+  if (pl->g - 1 > 32) {
+    set_error("coreset group size %d > 33 not supported by the warp-level selection kernel", pl->g);
+    return fail(VB_ERR_UNSUPPORTED);
+  }
+  if (d.text_len < 0 || d.text_valid < 0 || d.text_valid > d.text_len) {
+    set_error("text_valid %d must be within [0, text_len %d]", d.text_valid, d.text_len);
+    return fail(VB_ERR_INVALID);
+  }
+  for (int i = 0; i < 3; ++i) pl->nt[i] = d.latent[i] / d.tile[i];
+  pl->n_tiles = pl->nt[0] * pl->nt[1] * pl->nt[2];
+  pl->tile_tokens = d.tile[0] * d.tile[1] * d.tile[2];
+
+  // ---- coreset groups (coreset_select.py:31-54): raster group order, raster member order
+  const int fw = d.lowres_window[0], hw = d.lowres_window[1], ww = d.lowres_window[2];
+  const int center_slot = (fw / 2) * hw * ww + (hw / 2) * ww + ww / 2;
+  pl->center.resize(pl->G);
+  pl->margin.resize(static_cast<size_t>(pl->G) * (pl->g - 1));
+  std::vector<int32_t> center32(pl->G), margin32(pl->margin.size());
+  for (int gf = 0; gf < fg; ++gf)
+    for (int gh = 0; gh < hg; ++gh)
+      for (int gw = 0; gw < wg; ++gw) {
+        const int grp = (gf * hg + gh) * wg + gw;
+        int slot = 0, mi = 0;
+        for (int f = 0; f < fw; ++f)
+          for (int h = 0; h < hw; ++h)
+            for (int w = 0; w < ww; ++w, ++slot) {
+              const int tok = ((gf * fw + f) * d.latent[1] + (gh * hw + h)) * d.latent[2] + (gw * ww + w);
+              if (slot == center_slot) {
+                pl->center[grp] = tok;
+                center32[grp] = tok;
+              } else {
+                pl->margin[static_cast<size_t>(grp) * (pl->g - 1) + mi] = tok;
+                margin32[static_cast<size_t>(grp) * (pl->g - 1) + mi] = tok;
+                ++mi;
+              }
+            }
+      }
+
+  // ---- tile-major map (tile.py:26-29): position (tile_id * tau + intra) -> raster token; text rows keep theirs
+  pl->tile_map.resize(pl->S + d.text_len);
+  {
+    int pos = 0;
+    for (int a = 0; a < pl->nt[0]; ++a)
+      for (int b = 0; b < pl->nt[1]; ++b)
+        for (int c = 0; c < pl->nt[2]; ++c)
+          for (int x = 0; x < d.tile[0]; ++x)
+            for (int y = 0; y < d.tile[1]; ++y)
+              for (int z = 0; z < d.tile[2]; ++z)
+                pl->tile_map[pos++] =
+                    ((a * d.tile[0] + x) * d.latent[1] + (b * d.tile[1] + y)) * d.latent[2] + (c * d.tile[2] + z);
+    for (int i = 0; i < d.text_len; ++i) pl->tile_map[pl->S + i] = pl->S + i;
+  }
+
+  // device copies only when a device exists: geometry queries / exports also work on a CPU-only host
+  int count = 0;
+  if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0) {
+    pl->has_device = true;
+    auto up = [&](int32_t** dptr, const std::vector<int32_t>& v) -> int {
+      if (v.empty()) return VB_OK;
+      VB_CUDA_OK(cudaMalloc(dptr, v.size() * sizeof(int32_t)));
+      VB_CUDA_OK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      return VB_OK;
+    };
+    int rc;
+    if ((rc = up(&pl->d_center_tok, center32)) != VB_OK || (rc = up(&pl->d_margin_tok, margin32)) != VB_OK ||
+        (rc = up(&pl->d_tile_map, pl->tile_map)) != VB_OK) {
+      vb_plan_destroy(pl);
+      return rc;
+    }
+  } else {
+    cudaGetLastError();
+  }
+  int rc = build_text_dependent(pl);
+  if (rc != VB_OK) {
+    vb_plan_destroy(pl);
+    return rc;
+  }
+  *out = pl;
+  return VB_OK;
+}
+
+void vb_plan_destroy(vb_plan* pl) {
+  if (pl == nullptr) return;
+  pl->full.release();
+  pl->coreset.release();
+  pl->sliding.release();
+  if (pl->d_center_tok) cudaFree(pl->d_center_tok);
+  if (pl->d_margin_tok) cudaFree(pl->d_margin_tok);
+  if (pl->d_tile_map) cudaFree(pl->d_tile_map);
+  delete pl;
+}
+
+int vb_plan_set_text_valid(vb_plan* pl, int32_t text_valid) {
+  VB_REQUIRE(pl != nullptr, VB_ERR_INVALID, "null plan");
+  VB_REQUIRE(text_valid >= 0 && text_valid <= pl->d.text_len, VB_ERR_INVALID,
+             "text_valid %d must be within [0, text_len %d]", text_valid, pl->d.text_len);
+  if (text_valid == pl->d.text_valid) return VB_OK;
+  if (pl->has_device) VB_CUDA_OK(cudaDeviceSynchronize());   // tables may still be in use by earlier launches
+  pl->d.text_valid = text_valid;
+  return build_text_dependent(pl);
+}
+
+int vb_plan_query(const vb_plan* pl, int what, int64_t* value) {
+  VB_REQUIRE(pl != nullptr && value != nullptr, VB_ERR_INVALID, "null argument");
+  switch (what) {
+    case VB_PLAN_SEQ_LEN: *value = pl->S; break;
+    case VB_PLAN_NUM_GROUPS: *value = pl->G; break;
+    case VB_PLAN_GROUP_SIZE: *value = pl->g; break;
+    case VB_PLAN_CORESET_LEN: *value = pl->S_c; break;
+    case VB_PLAN_NUM_TILES: *value = pl->n_tiles; break;
+    case VB_PLAN_TILE_TOKENS: *value = pl->tile_tokens; break;
+    case VB_PLAN_NUM_POOLED: *value = pl->n_p; break;
+    case VB_PLAN_KEYS_PER_QUERY: *value = pl->keys_per_query; break;
+    case VB_PLAN_SLIDING_PAIRS: *value = static_cast<int64_t>(pl->sliding.pairs.size()); break;
+    case VB_PLAN_SLIDING_RUNS: *value = static_cast<int64_t>(pl->sliding.runs.size()); break;
+    default: VB_REQUIRE(false, VB_ERR_INVALID, "unknown plan query %d", what);
+  }
+  return VB_OK;
+}
+
+int vb_plan_export(const vb_plan* pl, int what, void* dst, int64_t* bytes) {
+  VB_REQUIRE(pl != nullptr && bytes != nullptr, VB_ERR_INVALID, "null argument");
+  const void* src = nullptr;
+  int64_t n = 0;
+  switch (what) {
+    case VB_EXPORT_CENTER_INDICES: src = pl->center.data(); n = pl->center.size() * sizeof(int64_t); break;
+    case VB_EXPORT_MARGIN_INDICES: src = pl->margin.data(); n = pl->margin.size() * sizeof(int64_t); break;
+    case VB_EXPORT_TILE_MAP: src = pl->tile_map.data(); n = pl->tile_map.size() * sizeof(int32_t); break;
+    case VB_EXPORT_TILE_WINDOW: src = pl->tile_window.data(); n = pl->tile_window.size() * sizeof(int32_t); break;
+    case VB_EXPORT_SLIDING_RUNS: src = pl->sliding.runs.data(); n = pl->sliding.runs.size() * sizeof(KvRun); break;
+    default: VB_REQUIRE(false, VB_ERR_INVALID, "unknown plan export %d", what);
+  }
+  if (dst != nullptr) {
+    VB_REQUIRE(*bytes >= n, VB_ERR_INVALID, "export buffer too small: %lld < %lld", (long long)*bytes, (long long)n);
+    memcpy(dst, src, n);
+  }
+  *bytes = n;
+  return VB_OK;
+}
+
+int vb_router_forward(const void* temb, int temb_dtype, const void* w, const void* bias, int w_dtype,
+                      int64_t w_layer_stride, int64_t bias_layer_stride, int32_t n_layers, int32_t batch,
+                      int32_t embed_dim, int32_t heads, float tau, float* scores, int32_t* branch,
+                      vb_stream_t stream) {
+  VB_REQUIRE(temb && w && bias && scores, VB_ERR_INVALID, "null argument");
+  int rc = launch_router(temb, temb_dtype, w, bias, w_dtype, w_layer_stride, bias_layer_stride, n_layers, batch,
+                         embed_dim, heads, tau, scores, branch, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+
+int vb_coreset_select(const vb_plan* pl, const void* x, int64_t stride_b, int64_t stride_h, int64_t stride_s,
+                      int32_t batch, int32_t heads, int64_t* unpooled_argsort, int64_t* pooled_argsort,
+                      int32_t* kept_tok, int32_t* dropped_tok, vb_stream_t stream) {
+  VB_REQUIRE(pl && x, VB_ERR_INVALID, "null argument");
+  VB_REQUIRE(pl->has_device, VB_ERR_UNSUPPORTED, "no CUDA device: vorta_b200 has no CPU path");
+  VB_REQUIRE(stride_s % 8 == 0 && stride_h % 8 == 0 && stride_b % 8 == 0, VB_ERR_INVALID,
+             "strides must be multiples of 8 elements");
+  SelectParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.stride_b = stride_b; p.stride_h = stride_h; p.stride_s = stride_s;
+  p.center_tok = pl->d_center_tok; p.margin_tok = pl->d_margin_tok; p.head_list = nullptr;
+  p.batch = batch; p.heads = heads; p.G = pl->G; p.n_margin = pl->g - 1; p.n_unpooled = pl->n_u;
+  p.seq_len = pl->S; p.text_len = pl->d.text_len;
+  p.unpooled_argsort = unpooled_argsort; p.pooled_argsort = pooled_argsort;
+  p.kept_tok = kept_tok; p.dropped_tok = dropped_tok;
+  int rc = launch_coreset_select(p, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+
+int vb_gather_rows(const void* src, int64_t src_stride_b, int64_t src_stride_h, int64_t src_stride_s, void* dst,
+                   int64_t dst_stride_b, int64_t dst_stride_h, int64_t dst_stride_s, const int32_t* map,
+                   int64_t map_stride_b, int64_t map_stride_h, int32_t batch, int32_t heads, int32_t n_rows,
+                   vb_stream_t stream) {
+  VB_REQUIRE(src && dst, VB_ERR_INVALID, "null argument");
+  GatherParams p;
+  memset(&p, 0, sizeof(p));
+  p.src[0] = static_cast<const __nv_bfloat16*>(src);
+  p.dst[0] = static_cast<__nv_bfloat16*>(dst);
+  p.src_stride[0][0] = src_stride_b; p.src_stride[0][1] = src_stride_h; p.src_stride[0][2] = src_stride_s;
+  p.dst_stride[0] = dst_stride_b; p.dst_stride[1] = dst_stride_h; p.dst_stride[2] = dst_stride_s;
+  p.map = map; p.map_stride_b = map_stride_b; p.map_stride_h = map_stride_h;
+  p.head_list = nullptr; p.n_tensors = 1; p.batch = batch; p.heads = heads; p.n_rows = n_rows;
+  int rc = launch_gather_rows(p, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+
+// ---- attention orchestration --------------------------------------------------------------------
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int64_t vb_attn_workspace_bytes(const vb_plan* pl, int32_t batch, int32_t heads) {
+  if (pl == nullptr) return 0;
+  const int64_t rows_s = pl->S + pl->d.text_len;            // sliding: tile-major copy of q, k, v
+  const int64_t rows_c = pl->S_c + pl->d.text_len;          // coreset: pooled q, k, v
+  const int64_t bh = static_cast<int64_t>(batch) * heads;
+  int64_t bytes = 0;
+  bytes += 3 * align_up(bh * rows_s * kHeadDim * 2, 1024);
+  bytes += 3 * align_up(bh * rows_c * kHeadDim * 2, 1024);
+  bytes += 2 * align_up(bh * rows_c * 4, 1024);                              // kept_tok for Q and K matchings
+  bytes += 2 * align_up(bh * static_cast<int64_t>(pl->G) * std::max(pl->n_p, 1) * 4, 1024);   // dropped_tok
+  bytes += 2 * align_up(static_cast<int64_t>(heads) * 4, 1024);              // head lists
+  return bytes + 4096;
+}
+
+namespace {
+struct Carver {
+  uint8_t* base;
+  int64_t off, cap;
+  void* take(int64_t bytes) {
+    off = align_up(off, 1024);
+    void* p = base + off;
+    off += bytes;
+    return off <= cap ? p : nullptr;
+  }
+};
+
+struct BranchLaunch {
+  const __nv_bfloat16 *q, *k, *v;
+  int64_t qs[3], ks[3], vs[3];   // b, h, s strides
+  int64_t n_rows_q, n_rows_kv, n_heads_tensor;
+  const Schedule* sched;
+  const int32_t* out_map;
+  int64_t out_map_stride_b, out_map_stride_h;
+  const int32_t* bcast_map;
+  int64_t bcast_stride_b, bcast_stride_h;
+  int32_t bcast_rows, bcast_n;
+};
+}  // namespace
+
+// Launch one branch for the head slots in `heads` (<= kMaxHeads per launch).
+static int run_branch(const BranchLaunch& bl, const vb_attn_args& a, const std::vector<AttnHead>& heads, int batch0,
+                      int nbatch, cudaStream_t stream) {
+  if (heads.empty() || bl.sched->pairs.empty()) return VB_OK;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_qkv_tensor_map(&mq, bl.q, bl.n_rows_q, bl.n_heads_tensor, a.batch, bl.qs[0], bl.qs[1], bl.qs[2])))
+    return rc;
+  if ((rc = make_qkv_tensor_map(&mk, bl.k, bl.n_rows_kv, bl.n_heads_tensor, a.batch, bl.ks[0], bl.ks[1], bl.ks[2])))
+    return rc;
+  if ((rc = make_qkv_tensor_map(&mv, bl.v, bl.n_rows_kv, bl.n_heads_tensor, a.batch, bl.vs[0], bl.vs[1], bl.vs[2])))
+    return rc;
+  for (size_t h0 = 0; h0 < heads.size(); h0 += kMaxHeads) {
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.pairs = bl.sched->d_pairs;
+    p.runs = bl.sched->d_runs;
+    p.out = static_cast<__nv_bfloat16*>(a.out);
+    p.out_stride_b = a.out_stride[0]; p.out_stride_h = a.out_stride[1]; p.out_stride_s = a.out_stride[2];
+    p.out_map = bl.out_map; p.out_map_stride_b = bl.out_map_stride_b; p.out_map_stride_h = bl.out_map_stride_h;
+    p.bcast_map = bl.bcast_map; p.bcast_stride_b = bl.bcast_stride_b; p.bcast_stride_h = bl.bcast_stride_h;
+    p.bcast_rows = bl.bcast_rows; p.bcast_n = bl.bcast_n;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+    p.batch0 = batch0;
+    p.dbg = a.debug;
+    if (a.debug != nullptr) {   // bring-up only: descriptor stride overrides for the V operand
+      if (const char* e = getenv("VB_DBG_V_LBO")) p.dbg_v_lbo = static_cast<uint32_t>(atoi(e));
+      if (const char* e = getenv("VB_DBG_V_SBO")) p.dbg_v_sbo = static_cast<uint32_t>(atoi(e));
+    }
+    const int n = static_cast<int>(std::min<size_t>(kMaxHeads, heads.size() - h0));
+    p.n_heads = n;
+    for (int i = 0; i < n; ++i) p.heads[i] = heads[h0 + i];
+    rc = launch_attn(mq, mk, mv, p, static_cast<int>(bl.sched->pairs.size()), n, nbatch, stream);
+    if (rc != VB_OK) return rc;
+    ++g_launches;
+    g_flops += bl.sched->flops_per_head * n * nbatch;
+  }
+  return VB_OK;
+}
+
+int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
+  VB_REQUIRE(pl != nullptr && args != nullptr, VB_ERR_INVALID, "null argument");
+  VB_REQUIRE(pl->has_device, VB_ERR_UNSUPPORTED, "no CUDA device: vorta_b200 has no CPU path");
+  const vb_attn_args& a = *args;
+  VB_REQUIRE(a.q && a.k && a.v && a.out, VB_ERR_INVALID, "null tensor");
+  VB_REQUIRE(a.batch > 0 && a.heads > 0, VB_ERR_INVALID, "batch and heads must be positive");
+  VB_REQUIRE(a.weights != nullptr || a.branch != nullptr, VB_ERR_INVALID, "need branch ids or blend weights");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool blend = a.weights != nullptr;
+  const int S = pl->S, TL = pl->d.text_len, TV = pl->d.text_valid;
+  const int N = S + TL;
+
+  // heads of each branch, ascending head order (wan.py:409 torch.nonzero)
+  std::vector<int32_t> by_branch[3];
+  for (int h = 0; h < a.heads; ++h) {
+    if (blend) {
+      for (int e = 0; e < 3; ++e) by_branch[e].push_back(h);
+    } else {
+      const int e = a.branch[h];
+      if (e == VB_BRANCH_SKIP) continue;
+      VB_REQUIRE(e >= 0 && e < 3, VB_ERR_INVALID, "branch id %d of head %d out of range", e, h);
+      by_branch[e].push_back(h);
+    }
+  }
+  const int64_t need = vb_attn_workspace_bytes(pl, a.batch, a.heads);
+  const bool needs_ws = !by_branch[1].empty() || !by_branch[2].empty();
+  VB_REQUIRE(!needs_ws || (a.workspace != nullptr && a.workspace_bytes >= need), VB_ERR_INVALID,
+             "workspace too small: %lld < %lld bytes", (long long)a.workspace_bytes, (long long)need);
+  Carver ws{static_cast<uint8_t*>(a.workspace), 0, a.workspace_bytes};
+  int rc;
+
+  auto head_entries = [&](const std::vector<int32_t>& hs, int e, bool slot_is_index, int b) {
+    std::vector<AttnHead> v(hs.size());
+    for (size_t i = 0; i < hs.size(); ++i) {
+      v[i].hk = slot_is_index ? static_cast<int32_t>(i) : hs[i];
+      v[i].ho = hs[i];
+      v[i].weight = blend ? a.weights[(static_cast<int64_t>(b) * a.heads + hs[i]) * 3 + e] : 1.f;
+      v[i].flags = (blend && e > 0) ? 1 : 0;
+    }
+    return v;
+  };
+  auto upload_heads = [&](const std::vector<int32_t>& hs, int32_t** d_list) -> int {
+    *d_list = static_cast<int32_t*>(ws.take(static_cast<int64_t>(hs.size()) * 4));
+    VB_REQUIRE(*d_list != nullptr, VB_ERR_INVALID, "workspace exhausted");
+    VB_CUDA_OK(cudaMemcpyAsync(*d_list, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, stream));
+    return VB_OK;
+  };
+  // blend weights differ per batch element; top-1 routing is shared by the batch (wan.py:398)
+  auto for_batches = [&](const BranchLaunch& bl, const std::vector<int32_t>& hs, int e, bool slot_is_index) -> int {
+    if (!blend) return run_branch(bl, a, head_entries(hs, e, slot_is_index, 0), 0, a.batch, stream);
+    for (int b = 0; b < a.batch; ++b) {
+      int r = run_branch(bl, a, head_entries(hs, e, slot_is_index, b), b, 1, stream);
+      if (r != VB_OK) return r;
+    }
+    return VB_OK;
+  };
+
+  // ---------------- branch 0: full attention, straight from the caller's tensors ----------------
+  if (!by_branch[0].empty()) {
+    BranchLaunch bl;
+    memset(&bl, 0, sizeof(bl));
+    bl.q = static_cast<const __nv_bfloat16*>(a.q);
+    bl.k = static_cast<const __nv_bfloat16*>(a.k);
+    bl.v = static_cast<const __nv_bfloat16*>(a.v);
+    for (int i = 0; i < 3; ++i) { bl.qs[i] = a.q_stride[i]; bl.ks[i] = a.k_stride[i]; bl.vs[i] = a.v_stride[i]; }
+    bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = a.heads;
+    bl.sched = &pl->full;
+    if ((rc = for_batches(bl, by_branch[0], 0, false)) != VB_OK) return rc;
+  }
+
+  // ---------------- branch 1: coreset ----------------
+  if (!by_branch[1].empty()) {
+    const std::vector<int32_t>& hs = by_branch[1];
+    const int nh = static_cast<int>(hs.size());
+    const int64_t rows = pl->S_c + TL;
+    const int64_t bh = static_cast<int64_t>(a.batch) * nh;
+    __nv_bfloat16* pq = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+    __nv_bfloat16* pk = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+    __nv_bfloat16* pv = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+    int32_t* kept_q = static_cast<int32_t*>(ws.take(bh * rows * 4));
+    int32_t* drop_q = static_cast<int32_t*>(ws.take(bh * pl->G * std::max(pl->n_p, 1) * 4));
+    int32_t* kept_k = kept_q;
+    const bool kv_from_k = (a.flags & VB_ATTN_CORESET_KV_FROM_K) != 0;
+    if (kv_from_k) kept_k = static_cast<int32_t*>(ws.take(bh * rows * 4));
+    int32_t* d_heads = nullptr;
+    if ((rc = upload_heads(hs, &d_heads)) != VB_OK) return rc;
+    VB_REQUIRE(pq && pk && pv && kept_q && drop_q && kept_k, VB_ERR_INVALID, "workspace exhausted");
+
+    SelectParams sp;
+    sp.x = static_cast<const __nv_bfloat16*>(a.q);
+    sp.stride_b = a.q_stride[0]; sp.stride_h = a.q_stride[1]; sp.stride_s = a.q_stride[2];
+    sp.center_tok = pl->d_center_tok; sp.margin_tok = pl->d_margin_tok; sp.head_list = d_heads;
+    sp.batch = a.batch; sp.heads = nh; sp.G = pl->G; sp.n_margin = pl->g - 1; sp.n_unpooled = pl->n_u;
+    sp.seq_len = S; sp.text_len = TL;
+    sp.unpooled_argsort = nullptr; sp.pooled_argsort = nullptr; sp.kept_tok = kept_q; sp.dropped_tok = drop_q;
+    if ((rc = launch_coreset_select(sp, stream)) != VB_OK) return rc;
+    ++g_launches;
+    if (kv_from_k) {
+      sp.x = static_cast<const __nv_bfloat16*>(a.k);
+      sp.stride_b = a.k_stride[0]; sp.stride_h = a.k_stride[1]; sp.stride_s = a.k_stride[2];
+      sp.kept_tok = kept_k; sp.dropped_tok = nullptr;
+      if ((rc = launch_coreset_select(sp, stream)) != VB_OK) return rc;
+      ++g_launches;
+    }
+    // pooled sequences [centres | kept margins | text]
+    GatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.dst_stride[0] = nh * rows * kHeadDim; gp.dst_stride[1] = rows * kHeadDim; gp.dst_stride[2] = kHeadDim;
+    gp.map_stride_b = nh * rows; gp.map_stride_h = rows;
+    gp.head_list = d_heads; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
+    if (!kv_from_k) {
+      gp.n_tensors = 3; gp.map = kept_q;
+      gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = pq;
+      gp.src[1] = static_cast<const __nv_bfloat16*>(a.k); gp.dst[1] = pk;
+      gp.src[2] = static_cast<const __nv_bfloat16*>(a.v); gp.dst[2] = pv;
+      for (int i = 0; i < 3; ++i) {
+        gp.src_stride[0][i] = a.q_stride[i]; gp.src_stride[1][i] = a.k_stride[i]; gp.src_stride[2][i] = a.v_stride[i];
+      }
+      if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
+      ++g_launches;
+    } else {
+      gp.n_tensors = 1; gp.map = kept_q;
+      gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = pq;
+      for (int i = 0; i < 3; ++i) gp.src_stride[0][i] = a.q_stride[i];
+      if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
+      gp.n_tensors = 2; gp.map = kept_k;
+      gp.src[0] = static_cast<const __nv_bfloat16*>(a.k); gp.dst[0] = pk;
+      gp.src[1] = static_cast<const __nv_bfloat16*>(a.v); gp.dst[1] = pv;
+      for (int i = 0; i < 3; ++i) { gp.src_stride[0][i] = a.k_stride[i]; gp.src_stride[1][i] = a.v_stride[i]; }
+      if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
+      g_launches += 2;
+    }
+    BranchLaunch bl;
+    memset(&bl, 0, sizeof(bl));
+    bl.q = pq; bl.k = pk; bl.v = pv;
+    const int64_t st[3] = {nh * rows * kHeadDim, rows * kHeadDim, kHeadDim};
+    for (int i = 0; i < 3; ++i) { bl.qs[i] = st[i]; bl.ks[i] = st[i]; bl.vs[i] = st[i]; }
+    bl.n_rows_q = pl->S_c + TV; bl.n_rows_kv = pl->S_c + TV; bl.n_heads_tensor = nh;
+    bl.sched = &pl->coreset;
+    bl.out_map = kept_q; bl.out_map_stride_b = nh * rows; bl.out_map_stride_h = rows;
+    if (pl->n_p > 0) {   // dropped margins receive their centre's output (coreset_select.py:157)
+      bl.bcast_map = drop_q; bl.bcast_stride_b = static_cast<int64_t>(nh) * pl->G * pl->n_p;
+      bl.bcast_stride_h = static_cast<int64_t>(pl->G) * pl->n_p; bl.bcast_rows = pl->G; bl.bcast_n = pl->n_p;
+    }
+    if ((rc = for_batches(bl, hs, 1, true)) != VB_OK) return rc;
+  }
+
+  // ---------------- branch 2: sliding tile ----------------
+  if (!by_branch[2].empty()) {
+    const std::vector<int32_t>& hs = by_branch[2];
+    const int nh = static_cast<int>(hs.size());
+    const int64_t rows = N;
+    const int64_t bh = static_cast<int64_t>(a.batch) * nh;
+    __nv_bfloat16* tq = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+    __nv_bfloat16* tk = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+    __nv_bfloat16* tv = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+    int32_t* d_heads = nullptr;
+    if ((rc = upload_heads(hs, &d_heads)) != VB_OK) return rc;
+    VB_REQUIRE(tq && tk && tv, VB_ERR_INVALID, "workspace exhausted");
+    GatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.n_tensors = 3; gp.map = pl->d_tile_map; gp.map_stride_b = 0; gp.map_stride_h = 0;
+    gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = tq;
+    gp.src[1] = static_cast<const __nv_bfloat16*>(a.k); gp.dst[1] = tk;
+    gp.src[2] = static_cast<const __nv_bfloat16*>(a.v); gp.dst[2] = tv;
+    for (int i = 0; i < 3; ++i) {
+      gp.src_stride[0][i] = a.q_stride[i]; gp.src_stride[1][i] = a.k_stride[i]; gp.src_stride[2][i] = a.v_stride[i];
+    }
+    gp.dst_stride[0] = nh * rows * kHeadDim; gp.dst_stride[1] = rows * kHeadDim; gp.dst_stride[2] = kHeadDim;
+    gp.head_list = d_heads; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
+    if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
+    ++g_launches;
+    BranchLaunch bl;
+    memset(&bl, 0, sizeof(bl));
+    bl.q = tq; bl.k = tk; bl.v = tv;
+    const int64_t st[3] = {nh * rows * kHeadDim, rows * kHeadDim, kHeadDim};
+    for (int i = 0; i < 3; ++i) { bl.qs[i] = st[i]; bl.ks[i] = st[i]; bl.vs[i] = st[i]; }
+    bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = nh;
+    bl.sched = &pl->sliding;
+    bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
+    if ((rc = for_batches(bl, hs, 2, true)) != VB_OK) return rc;
+  }
+
+  // ---------------- padded text queries produce zeros (hunyuan.py:176; flex fully-masked rows) ----------------
+  if (TL > TV) {
+    rc = launch_zero_rows(static_cast<__nv_bfloat16*>(a.out), a.out_stride[0], a.out_stride[1], a.out_stride[2],
+                          a.batch, a.heads, S + TV, TL - TV, stream);
+    if (rc != VB_OK) return rc;
+    ++g_launches;
+  }
+  return VB_OK;
+}
+
+void vb_stats_reset(void) {
+  g_launches = 0;
+  g_flops = 0.0;
+}
+int64_t vb_stats_launches(void) { return g_launches; }
+double vb_stats_attn_flops(void) { return g_flops; }
+
+int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t heads, int32_t world, int32_t n_tensors,
+                          int64_t x_tensor_stride, int64_t send_tensor_stride, vb_stream_t stream) {
+  VB_REQUIRE(x && send, VB_ERR_INVALID, "null argument");
+  int rc = launch_ulysses_permute(x, send, s_loc, heads, world, n_tensors, x_tensor_stride, send_tensor_stride, 1,
+                                  static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
+                            vb_stream_t stream) {
+  VB_REQUIRE(recv && y, VB_ERR_INVALID, "null argument");
+  int rc = launch_ulysses_permute(recv, y, s_loc, heads, world, 1, 0, 0, 0, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// vb_attn.cu — tcgen05 / TMEM / TMA flash-attention forward for sm_100a, driven by key/value *run lists*.
+//
+// One kernel serves all three VORTA branches (reference: vorta/attention/wan.py:103-149 SDPA, :243-270 coreset,
+// :272-294 sliding tile).  A CTA owns up to two 128-row query tiles that attend to the same list of contiguous
+// key ranges ("runs", in kernel order):
+//     full     : one run [0, N)
+//     coreset  : one run [0, S_c (+ text))   over the pooled sequence
+//     sliding  : the <= 9 (+1 text) runs of the 3-D tile window, tile-major order
+// so the block-sparse schedule is just a different table, and masked 3-D tiles are never visited.
+//
+// Warp roles (320 threads):
+//     warps 0-3 : softmax + correction + epilogue for query tile 0 (one thread per query row / TMEM lane)
+//     warps 4-7 : same for query tile 1
+//     warp  8   : TMA producer (Q tiles once, then K/V blocks through a 5-slot ring of 32 KB)
+//     warp  9   : tcgen05.mma issuer (+ TMEM allocation)
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (bf16) overwrites the first 64
+// columns of its S.  S = Q K^T is an SS UMMA (both operands K-major, SWIZZLE_128B as written by TMA), O += P V is
+// a TS UMMA (P from TMEM, V from shared memory, MN-major).  While the softmax warps of one tile work on S_t(j),
+// the tensor pipe runs PV and the next QK of the other tile.
+#include "vb_common.cuh"
+#include "vb_ptx.cuh"
+
+namespace vb {
+
+constexpr int kNumSlots = 5;                       // K/V ring
+constexpr int kTileBytes = kBlockN * kHeadDim * 2; // 32 KB: one 128x128 bf16 block = two 128x64 swizzled halves
+constexpr int kHalfBytes = kTileBytes / 2;
+constexpr int kAttnThreads = 320;
+constexpr int kAttnSmemBytes = 2 * kTileBytes + kNumSlots * kTileBytes + 1024;  // + alignment slack
+constexpr float kRescaleThreshold = 8.0f;          // lazy rescale: tolerate 2^8 growth before touching O
+
+struct BlockWalker {
+  const KvRun* runs;
+  int n_runs, r, off;
+  __device__ __forceinline__ BlockWalker(const KvRun* rr, int n) : runs(rr), n_runs(n), r(0), off(0) {}
+  // next 128-key block: first key row and number of valid keys; false when exhausted
+  __device__ __forceinline__ bool next(int& row0, int& valid) {
+    while (r < n_runs) {
+      const int len = runs[r].len;
+      if (off < len) {
+        row0 = runs[r].start + off;
+        valid = min(kBlockN, len - off);
+        off += kBlockN;
+        return true;
+      }
+      ++r;
+      off = 0;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ int count_blocks(const KvRun* runs, int n_runs) {
+  int n = 0;
+  for (int r = 0; r < n_runs; ++r) n += (runs[r].len + kBlockN - 1) / kBlockN;
+  return n;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_q_full[2];
+  __shared__ uint64_t bar_slot_full[kNumSlots];
+  __shared__ uint64_t bar_slot_empty[kNumSlots];
+  __shared__ uint64_t bar_s_full[2];
+  __shared__ uint64_t bar_p_ready[2];
+  __shared__ uint64_t bar_o_full[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ KvRun s_runs[32];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const QPair pair = p.pairs[blockIdx.x];
+  const AttnHead head = p.heads[blockIdx.y];
+  const int batch = blockIdx.z + p.batch0;
+  const int nq = pair.nq;
+
+  // 1024-byte aligned operand area (SWIZZLE_128B atoms are 8 rows x 128 B)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_q = smem;                       // 2 x 32 KB
+  uint8_t* smem_kv = smem + 2 * kTileBytes;     // kNumSlots x 32 KB
+
+  const int n_runs = min(pair.run_count, 32);
+  if (threadIdx.x < n_runs) s_runs[threadIdx.x] = p.runs[pair.run_begin + threadIdx.x];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q_full[i], 1);
+      mbar_init(&bar_s_full[i], 1);
+      mbar_init(&bar_p_ready[i], kBlockM);
+      mbar_init(&bar_o_full[i], 1);
+    }
+    for (int i = 0; i < kNumSlots; ++i) {
+      mbar_init(&bar_slot_full[i], 1);
+      mbar_init(&bar_slot_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 9) {
+    tmem_alloc(&tmem_base_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int n_blocks = count_blocks(s_runs, n_runs);
+
+  if (warp == 8) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      for (int t = 0; t < nq; ++t) {
+        mbar_arrive_expect_tx(&bar_q_full[t], kTileBytes);
+        tma_load_4d(smem_q + t * kTileBytes, &tmap_q, &bar_q_full[t], 0, pair.q_row0[t], head.hk, batch);
+        tma_load_4d(smem_q + t * kTileBytes + kHalfBytes, &tmap_q, &bar_q_full[t], 64, pair.q_row0[t], head.hk,
+                    batch);
+      }
+      BlockWalker w(s_runs, n_runs);
+      int row0, valid;
+      uint32_t load_idx = 0;
+      while (w.next(row0, valid)) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which, ++load_idx) {
+          const uint32_t slot = load_idx % kNumSlots;
+          const uint32_t phase = (load_idx / kNumSlots) & 1u;
+          mbar_wait(&bar_slot_empty[slot], phase ^ 1u);
+          mbar_arrive_expect_tx(&bar_slot_full[slot], kTileBytes);
+          const CUtensorMap* m = which == 0 ? &tmap_k : &tmap_v;
+          uint8_t* dst = smem_kv + slot * kTileBytes;
+          tma_load_4d(dst, m, &bar_slot_full[slot], 0, row0, head.hk, batch);
+          tma_load_4d(dst + kHalfBytes, m, &bar_slot_full[slot], 64, row0, head.hk, batch);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ======================================= MMA issuer =========================================
+    if (lane == 0 && n_blocks > 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
+      const uint32_t v_lbo = p.dbg_v_lbo ? p.dbg_v_lbo : (uint32_t)kHalfBytes;
+      const uint32_t v_sbo = p.dbg_v_sbo ? p.dbg_v_sbo : 1024u;
+
+      auto issue_qk = [&](int t, uint32_t slot) {
+        const uint32_t qa = smem_u32(smem_q + t * kTileBytes);
+        const uint32_t kb = smem_u32(smem_kv + slot * kTileBytes);
+        const uint32_t d = tmem_base + t * kBlockN;
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          // K-major, 64-element (128 B) swizzled rows: 16 elements = 32 B inside the atom, 64 elements = next half
+          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+          umma_ss(d, umma_smem_desc(qa + off, 16, 1024), umma_smem_desc(kb + off, 16, 1024), idesc_qk, k > 0);
+        }
+      };
+      auto issue_pv = [&](int t, uint32_t slot, uint32_t accumulate) {
+        const uint32_t vb_ = smem_u32(smem_kv + slot * kTileBytes);
+        const uint32_t d = tmem_base + 2 * kBlockN + t * kHeadDim;
+        const uint32_t a = tmem_base + t * kBlockN;     // P_t: packed bf16 pairs, 8 columns per 16 keys
+#pragma unroll
+        for (int k = 0; k < kBlockN / 16; ++k) {
+          // V block is [128 keys][128 d]: MN(d)-major, 16 keys = 16 rows x 128 B = 2048 B
+          umma_ts(d, a + k * 8, umma_smem_desc(vb_ + k * 2048, v_lbo, v_sbo), idesc_pv, accumulate | (k > 0));
+        }
+      };
+
+      for (int t = 0; t < nq; ++t) mbar_wait(&bar_q_full[t], 0);
+      mbar_wait(&bar_slot_full[0], 0);   // K(0) is load 0
+      tc_fence_after();
+      for (int t = 0; t < nq; ++t) {
+        issue_qk(t, 0);
+        umma_commit(&bar_s_full[t]);
+      }
+      umma_commit(&bar_slot_empty[0]);
+
+      for (int j = 0; j < n_blocks; ++j) {
+        const uint32_t v_idx = 2 * j + 1, v_slot = v_idx % kNumSlots, v_phase = (v_idx / kNumSlots) & 1u;
+        const uint32_t k_idx = 2 * j + 2, k_slot = k_idx % kNumSlots, k_phase = (k_idx / kNumSlots) & 1u;
+        const bool more = j + 1 < n_blocks;
+        mbar_wait(&bar_slot_full[v_slot], v_phase);
+        for (int t = 0; t < nq; ++t) {
+          mbar_wait(&bar_p_ready[t], j & 1);
+          tc_fence_after();
+          issue_pv(t, v_slot, j > 0);
+          if (more) {
+            if (t == 0) {
+              mbar_wait(&bar_slot_full[k_slot], k_phase);
+              tc_fence_after();
+            }
+            issue_qk(t, k_slot);
+            umma_commit(&bar_s_full[t]);
+          } else {
+            umma_commit(&bar_o_full[t]);
+          }
+        }
+        umma_commit(&bar_slot_empty[v_slot]);
+        if (more) umma_commit(&bar_slot_empty[k_slot]);
+      }
+    }
+  } else {
+    // ============================ softmax / correction / epilogue ===============================
+    const int t = warp >> 2;                         // query tile of this warpgroup
+    const int row = ((warp & 3) << 5) + lane;        // query row inside the tile == TMEM lane
+    if (t < nq && n_blocks > 0) {
+      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) << 5) << 16;
+      const uint32_t s_addr = tmem_base + lane_addr + t * kBlockN;
+      const uint32_t o_addr = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim;
+      const float scale = p.scale_log2;
+      float m_ref = 0.f, l_sum = 0.f;
+
+      BlockWalker w(s_runs, n_runs);
+      int row0, valid;
+      for (int j = 0; w.next(row0, valid); ++j) {
+        mbar_wait(&bar_s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t s[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, s[c]);
+        tmem_ld_wait();
+
+        if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+          float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN;   // raw scores of block 0
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(s[c][i]);
+        }
+
+        if (valid < kBlockN) {   // run tail: keys beyond the run do not exist for this query
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) s[c][i] = 0xff800000u;   // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[c][i + 0]));
+            mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+          }
+        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;   // valid >= 1, so finite
+
+        float alpha = 1.f;
+        bool rescale = false;
+        if (j == 0) {
+          m_ref = m_new;
+        } else {
+          const bool need = m_new > m_ref + kRescaleThreshold;
+          rescale = __any_sync(0xffffffffu, need);       // tcgen05.ld/st below are warp-collective
+          if (need) {
+            alpha = fast_exp2(m_ref - m_new);
+            m_ref = m_new;
+          }
+        }
+        l_sum *= alpha;
+
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = hp * 2 + cc;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float e0 = fast_exp2(fmaf(__uint_as_float(s[c][i + 0]), scale, -m_ref));
+              const float e1 = fast_exp2(fmaf(__uint_as_float(s[c][i + 1]), scale, -m_ref));
+              const float e2 = fast_exp2(fmaf(__uint_as_float(s[c][i + 2]), scale, -m_ref));
+              const float e3 = fast_exp2(fmaf(__uint_as_float(s[c][i + 3]), scale, -m_ref));
+              sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
+              pk[cc * 16 + (i >> 1) + 0] = pack_bf16x2(e0, e1);
+              pk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
+            }
+          }
+          tmem_st32(s_addr + hp * 32, pk);   // P_t(j): keys [64 hp, 64 hp + 64) -> 32 columns of bf16 pairs
+        }
+        l_sum += (sum0 + sum1) + (sum2 + sum3);
+
+        if (rescale) {
+          // PV_t(j-1) completed before S_t(j) was signalled (commit order), PV_t(j) waits for our arrive:
+          // O_t is quiescent here.
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr + c * 32, o);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_p_ready[t]);
+      }
+
+      // ------------------------------------ epilogue ------------------------------------
+      mbar_wait(&bar_o_full[t], 0);
+      tc_fence_after();
+      const bool row_ok = row < pair.q_rows[t];
+      const int krow = pair.q_row0[t] + row;      // row in kernel order
+      const float inv = head.weight / l_sum;
+      const bool accumulate = (head.flags & 1) != 0;
+      int n_dst = 0;
+      int64_t dst_tok = 0;
+      const int32_t* bc = nullptr;
+      if (row_ok) {
+        dst_tok = p.out_map ? p.out_map[batch * p.out_map_stride_b + head.hk * p.out_map_stride_h + krow] : krow;
+        n_dst = 1;
+        if (p.bcast_map != nullptr && krow < p.bcast_rows) {
+          bc = p.bcast_map + batch * p.bcast_stride_b + head.hk * p.bcast_stride_h +
+               static_cast<int64_t>(krow) * p.bcast_n;
+          n_dst += p.bcast_n;
+        }
+      }
+      __nv_bfloat16* out_head = p.out + batch * p.out_stride_b + head.ho * p.out_stride_h;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(o_addr + c * 32, o);
+        tmem_ld_wait();
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+          float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(o[i]);   // un-normalised O
+          if (c == 0) p.dbg[4 * kBlockM * kBlockN + t * kBlockM + row] = l_sum;
+        }
+        for (int dsti = 0; dsti < n_dst; ++dsti) {
+          const int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
+          uint4* dst = reinterpret_cast<uint4*>(out_head + tok * p.out_stride_s + c * 32);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q4 * 8 + i]) * inv;
+            if (accumulate) {
+              const uint4 prev = dst[q4];
+              const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[2 * i + 0] += __uint_as_float(pw[i] << 16);
+                f[2 * i + 1] += __uint_as_float(pw[i] & 0xffff0000u);
+              }
+            }
+            uint4 v;
+            v.x = pack_bf16x2(f[0], f[1]);
+            v.y = pack_bf16x2(f[2], f[3]);
+            v.z = pack_bf16x2(f[4], f[5]);
+            v.w = pack_bf16x2(f[6], f[7]);
+            dst[q4] = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map over (channel=128, token=n_rows, head, batch) with a (64, 128, 1, 1) box, SWIZZLE_128B.
+int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
+                        int64_t stride_b, int64_t stride_h, int64_t stride_s) {
+  PFN_encodeTiled enc = get_encode_fn();
+  VB_REQUIRE(enc != nullptr, VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, VB_ERR_INVALID, "tensor base must be 16-byte aligned");
+  VB_REQUIRE(stride_s % 8 == 0 && stride_h % 8 == 0 && stride_b % 8 == 0, VB_ERR_INVALID,
+             "token/head/batch strides must be multiples of 8 elements (16 bytes)");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(n_rows),
+                        static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(batch)};
+  // a size-1 dimension may carry a zero stride from the caller; TMA needs a positive multiple of 16 bytes
+  auto fix = [](int64_t s) { return static_cast<cuuint64_t>((s > 0 ? s : 8) * 2); };
+  cuuint64_t strides[3] = {fix(stride_s), fix(stride_h), fix(stride_b)};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(kBlockN), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VB_OK;
+}
+
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
+                int n_pairs, int n_heads, int batch, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    VB_CUDA_OK(cudaFuncSetAttribute(vb_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kAttnSmemBytes));
+    configured = true;
+  }
+  if (n_pairs == 0 || n_heads == 0 || batch == 0) return VB_OK;
+  dim3 grid(n_pairs, n_heads, batch);
+  vb_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(mq, mk, mv, params);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb

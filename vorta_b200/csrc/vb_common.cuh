@@ -1,0 +1,105 @@
+// vb_common.cuh — shared host-side helpers (error plumbing) and kernel-facing parameter structs.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vorta_b200.h"
+
+namespace vb {
+
+// thread-local last-error string returned by vb_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define VB_CUDA_OK(expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::vb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+      return VB_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define VB_REQUIRE(cond, code, ...)        \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::vb::set_error(__VA_ARGS__);        \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+constexpr int kHeadDim = 128;     // D of every supported model (Wan 1.3B/14B, HunyuanVideo)
+constexpr int kBlockM = 128;      // query rows per MMA tile (one TMEM lane per row)
+constexpr int kBlockN = 128;      // keys per MMA tile
+constexpr int kMaxHeads = 64;     // heads per attention launch
+
+// One CTA's work: up to two 128-row query tiles that share the same key/value run list.
+struct QPair {
+  int32_t q_row0[2];   // first row of each query tile, in kernel order
+  int32_t q_rows[2];   // valid rows in each tile (<= 128)
+  int32_t run_begin;   // first entry in KvRun[]
+  int32_t run_count;   // number of runs
+  int32_t nq;          // 1 or 2
+  int32_t pad;
+};
+// A contiguous range of keys (kernel order) every query of the pair attends to.
+struct KvRun {
+  int32_t start;
+  int32_t len;
+};
+struct AttnHead {
+  int32_t hk;       // head coordinate inside the Q/K/V tensor maps
+  int32_t ho;       // head index in the output tensor
+  float weight;     // epilogue scale (routing score in blend mode, 1 in top-1 mode)
+  int32_t flags;    // bit 0: accumulate into the existing output (blend of branches)
+};
+
+struct AttnParams {
+  const QPair* pairs;
+  const KvRun* runs;
+  __nv_bfloat16* out;
+  int64_t out_stride_b, out_stride_h, out_stride_s;   // elements
+  const int32_t* out_map;       // kernel row -> output token, nullptr = identity
+  int64_t out_map_stride_h;     // per-head stride of out_map (0 = shared by all heads), indexed by hk
+  int64_t out_map_stride_b;
+  const int32_t* bcast_map;     // rows < bcast_rows also write bcast_n copies (coreset unpool)
+  int64_t bcast_stride_h, bcast_stride_b;
+  int32_t bcast_rows, bcast_n;
+  float scale_log2;             // log2(e) / sqrt(D)
+  int32_t n_heads;
+  int32_t batch0;               // batch index of blockIdx.z == 0 (blend mode launches one batch at a time)
+  float* dbg;                   // optional debug dump (bring-up only), nullptr in production
+  uint32_t dbg_v_lbo, dbg_v_sbo;  // bring-up overrides of the V descriptor strides (0 = default)
+  AttnHead heads[kMaxHeads];
+};
+
+// Coreset selection launch parameters (vb_kernels.cu)
+struct SelectParams {
+  const __nv_bfloat16* x;
+  int64_t stride_b, stride_h, stride_s;
+  const int32_t* center_tok;   // (G)
+  const int32_t* margin_tok;   // (G, g-1)
+  const int32_t* head_list;    // source head of each processed head slot, nullptr = identity
+  int32_t batch, heads, G, n_margin, n_unpooled, seq_len, text_len;
+  int64_t* unpooled_argsort;   // (B, heads, G, n_u)
+  int64_t* pooled_argsort;     // (B, heads, G, n_margin - n_u)
+  int32_t* kept_tok;           // (B, heads, S_c + text_len)
+  int32_t* dropped_tok;        // (B, heads, G, n_margin - n_u)
+};
+// Row gather launch parameters: up to three tensors share one row map (vb_kernels.cu)
+struct GatherParams {
+  const __nv_bfloat16* src[3];
+  __nv_bfloat16* dst[3];
+  int64_t src_stride[3][3];   // [tensor][b, h, s]
+  int64_t dst_stride[3];      // b, h, s (shared by the tensors)
+  const int32_t* map;
+  int64_t map_stride_b, map_stride_h;
+  const int32_t* head_list;   // nullptr = identity
+  int32_t n_tensors, batch, heads, n_rows;
+};
+
+}  // namespace vb

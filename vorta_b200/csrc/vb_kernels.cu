@@ -1,0 +1,316 @@
+// vb_kernels.cu — the HBM-bound kernels of the path: coreset similarity selection, row gather (pooling and
+// tile-major layout), router head, zero-fill of padded text rows and the Ulysses pack / unpack passes.
+// These are byte / index kernels: 16-byte vector accesses, one warp per small work unit, grids in multiples of
+// the SM count.  No tensor cores here on purpose.
+#include "vb_common.cuh"
+
+namespace vb {
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void bf16x8_to_double(const uint4& v, double (&d)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    d[2 * i + 0] = static_cast<double>(__uint_as_float(w[i] << 16));
+    d[2 * i + 1] = static_cast<double>(__uint_as_float(w[i] & 0xffff0000u));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coreset selection (reference: vorta/attention/coreset_select.py:91-113)
+//   one warp per (batch, head, group); a half-warp (16 lanes x 16 B) streams one 256-byte token row, so two
+//   margin rows are in flight per step.  <c, m>, |m|^2 and |c|^2 accumulate in fp64; the cosine similarities of
+//   the g-1 margins are ranked by counting (ascending, ties -> lower margin position first).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelectWarps = 8;
+
+__global__ void __launch_bounds__(kSelectWarps * 32) vb_coreset_select_kernel(const SelectParams p) {
+  __shared__ double s_sim[kSelectWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, hl = lane & 15;
+  const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G;
+  const int n_p = p.n_margin - p.n_unpooled;
+  const int row_len = p.G * (1 + p.n_unpooled) + p.text_len;   // kept_tok row length
+
+  for (int64_t unit = static_cast<int64_t>(blockIdx.x) * kSelectWarps + warp; unit < total;
+       unit += static_cast<int64_t>(gridDim.x) * kSelectWarps) {
+    const int grp = static_cast<int>(unit % p.G);
+    const int hs = static_cast<int>((unit / p.G) % p.heads);
+    const int b = static_cast<int>(unit / (static_cast<int64_t>(p.G) * p.heads));
+    const int h_src = p.head_list ? p.head_list[hs] : hs;
+    const __nv_bfloat16* base = p.x + b * p.stride_b + h_src * p.stride_h;
+
+    // centre row: every half-warp holds the same 8 channels per lane
+    const int ctok = p.center_tok[grp];
+    double c[8];
+    bf16x8_to_double(ld_stream(reinterpret_cast<const uint4*>(base + ctok * p.stride_s) + hl), c);
+    double cn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cn = fma(c[i], c[i], cn);
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
+    const double c_norm = fmax(sqrt(cn), 1e-12);   // F.normalize eps
+
+    const int32_t* mtok = p.margin_tok + static_cast<int64_t>(grp) * p.n_margin;
+    for (int m0 = 0; m0 < p.n_margin; m0 += 2) {
+      const int m = m0 + half;
+      double dot = 0.0, mn = 0.0;
+      if (m < p.n_margin) {
+        double v[8];
+        bf16x8_to_double(ld_stream(reinterpret_cast<const uint4*>(base + mtok[m] * p.stride_s) + hl), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dot = fma(c[i], v[i], dot);
+          mn = fma(v[i], v[i], mn);
+        }
+      }
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        mn += __shfl_xor_sync(0xffffffffu, mn, o);
+      }
+      if (hl == 0 && m < p.n_margin) s_sim[warp][m] = dot / (c_norm * fmax(sqrt(mn), 1e-12));
+    }
+    __syncwarp();
+
+    if (lane < p.n_margin) {
+      const double mine = s_sim[warp][lane];
+      int rank = 0;
+      for (int j = 0; j < p.n_margin; ++j) {
+        const double o = s_sim[warp][j];
+        rank += (o < mine) || (o == mine && j < lane);
+      }
+      const int64_t bh = static_cast<int64_t>(b) * p.heads + hs;
+      const int tok = mtok[lane];
+      if (rank < p.n_unpooled) {
+        if (p.unpooled_argsort) p.unpooled_argsort[(bh * p.G + grp) * p.n_unpooled + rank] = lane;
+        if (p.kept_tok) p.kept_tok[bh * row_len + p.G + static_cast<int64_t>(grp) * p.n_unpooled + rank] = tok;
+      } else {
+        if (p.pooled_argsort) p.pooled_argsort[(bh * p.G + grp) * n_p + (rank - p.n_unpooled)] = lane;
+        if (p.dropped_tok) p.dropped_tok[(bh * p.G + grp) * n_p + (rank - p.n_unpooled)] = tok;
+      }
+      if (lane == 0 && p.kept_tok) p.kept_tok[bh * row_len + grp] = ctok;
+    }
+    // text rows keep their position behind the pooled video rows
+    if (p.kept_tok && grp == 0) {
+      const int64_t bh = static_cast<int64_t>(b) * p.heads + hs;
+      for (int i = lane; i < p.text_len; i += 32)
+        p.kept_tok[bh * row_len + p.G * (1 + p.n_unpooled) + i] = p.seq_len + i;
+    }
+    __syncwarp();
+  }
+}
+
+int launch_coreset_select(const SelectParams& p, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G;
+  if (total == 0) return VB_OK;
+  const int64_t blocks_needed = (total + kSelectWarps - 1) / kSelectWarps;
+  const int grid = static_cast<int>(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
+  vb_coreset_select_kernel<<<grid, kSelectWarps * 32, 0, stream>>>(p);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row gather: dst[t][b, hs, i, :] = src[t][b, head_list[hs], map[b, hs, i], :], up to 3 tensors per launch
+// (reference: coreset_select.py:91-93,118-123 pooling; tile.py:7-41 tile-major layout)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vb_gather_rows_kernel(const GatherParams p) {
+  // half-warp per row: 16 lanes x 16 B = one 256-byte row; 4 rows in flight per half-warp for latency hiding
+  const int lane16 = threadIdx.x & 15;
+  const int64_t hw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+  const int64_t n_hw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4;
+  const int64_t rows_per_tensor = static_cast<int64_t>(p.batch) * p.heads * p.n_rows;
+  const int64_t total = rows_per_tensor * p.n_tensors;
+  for (int64_t r0 = hw * 4; r0 < total; r0 += n_hw * 4) {
+    uint4 val[4];
+    uint4* dptr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u;
+      dptr[u] = nullptr;
+      if (r < total) {
+        const int t = static_cast<int>(r / rows_per_tensor);
+        int64_t rr = r % rows_per_tensor;
+        const int i = static_cast<int>(rr % p.n_rows);
+        rr /= p.n_rows;
+        const int hs = static_cast<int>(rr % p.heads);
+        const int b = static_cast<int>(rr / p.heads);
+        const int h_src = p.head_list ? p.head_list[hs] : hs;
+        const int src_row = p.map ? p.map[b * p.map_stride_b + hs * p.map_stride_h + i] : i;
+        const __nv_bfloat16* s = p.src[t] + b * p.src_stride[t][0] + h_src * p.src_stride[t][1] +
+                                 static_cast<int64_t>(src_row) * p.src_stride[t][2];
+        val[u] = ld_stream(reinterpret_cast<const uint4*>(s) + lane16);
+        dptr[u] = reinterpret_cast<uint4*>(p.dst[t] + b * p.dst_stride[0] + hs * p.dst_stride[1] +
+                                           static_cast<int64_t>(i) * p.dst_stride[2]) + lane16;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dptr[u]) *dptr[u] = val[u];
+  }
+}
+
+int launch_gather_rows(const GatherParams& p, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.n_rows * p.n_tensors;
+  if (total == 0) return VB_OK;
+  const int64_t blocks_needed = (total / 4 * 16 + 255) / 256 + 1;
+  const int grid = static_cast<int>(blocks_needed < 148 * 16 ? blocks_needed : 148 * 16);
+  vb_gather_rows_kernel<<<grid, 256, 0, stream>>>(p);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zero rows [row0, row0 + n) of every (batch, head): padded text queries produce 0 (hunyuan.py:176)
+// ------------------------------------------------------------------------------------------------
+__global__ void vb_zero_rows_kernel(__nv_bfloat16* out, int64_t sb, int64_t sh, int64_t ss, int batch, int heads,
+                                    int row0, int n_rows) {
+  const int64_t total = static_cast<int64_t>(batch) * heads * n_rows * 16;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 15);
+    int64_t r = i >> 4;
+    const int row = static_cast<int>(r % n_rows);
+    r /= n_rows;
+    const int h = static_cast<int>(r % heads);
+    const int b = static_cast<int>(r / heads);
+    reinterpret_cast<uint4*>(out + b * sb + h * sh + static_cast<int64_t>(row0 + row) * ss)[c] = make_uint4(0, 0, 0, 0);
+  }
+}
+int launch_zero_rows(__nv_bfloat16* out, int64_t sb, int64_t sh, int64_t ss, int batch, int heads, int row0,
+                     int n_rows, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(batch) * heads * n_rows * 16;
+  if (total == 0) return VB_OK;
+  const int grid = static_cast<int>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  vb_zero_rows_kernel<<<grid, 256, 0, stream>>>(out, sb, sh, ss, batch, heads, row0, n_rows);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Router (reference: vorta/patch/router.py:33-43 and wan.py:396-400), fp32, all layers of a step in one launch.
+//   grid (n_layers, batch); the block stages silu(temb[b]) in shared memory, warps own output rows.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TE, typename TW>
+__global__ void __launch_bounds__(256)
+vb_router_kernel(const TE* temb, const TW* w, const TW* bias, int64_t w_layer_stride, int64_t bias_layer_stride,
+                 int embed_dim, int heads, float tau, float* scores, int32_t* branch) {
+  extern __shared__ float s_buf[];   // embed_dim silu values, then 3*heads logits
+  float* s_act = s_buf;
+  float* s_logit = s_buf + embed_dim;
+  const int layer = blockIdx.x, b = blockIdx.y, batch = gridDim.y;
+  const int n_out = heads * 3;
+  for (int i = threadIdx.x; i < embed_dim; i += blockDim.x) {
+    const float x = to_f32(temb[static_cast<int64_t>(b) * embed_dim + i]);
+    s_act[i] = x / (1.f + expf(-x));   // SiLU
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const TW* wl = w + layer * w_layer_stride;
+  for (int o = warp; o < n_out; o += n_warps) {
+    const TW* row = wl + static_cast<int64_t>(o) * embed_dim;
+    float acc = 0.f;
+    for (int i = lane; i < embed_dim; i += 32) acc = fmaf(to_f32(row[i]), s_act[i], acc);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s_logit[o] = acc + to_f32(bias[layer * bias_layer_stride + o]);
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < heads; h += blockDim.x) {
+    const float l0 = s_logit[3 * h], l1 = s_logit[3 * h + 1], l2 = s_logit[3 * h + 2];
+    const float mx = fmaxf(l0, fmaxf(l1, l2));
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+    const float inv = 1.f / (e0 + e1 + e2);
+    const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+    float* sc = scores + ((static_cast<int64_t>(layer) * batch + b) * heads + h) * 3;
+    sc[0] = p0; sc[1] = p1; sc[2] = p2;
+    if (b == 0 && branch != nullptr) {   // the first sample decides for the whole batch (wan.py:398)
+      int best = 0;
+      float bs = p0;
+      if (p1 > bs) { best = 1; bs = p1; }
+      if (p2 > bs) { best = 2; bs = p2; }
+      if (bs < tau) best = 0;            // NaN tau compares false: no threshold
+      branch[layer * heads + h] = best;
+    }
+  }
+}
+
+int launch_router(const void* temb, int temb_dtype, const void* w, const void* bias, int w_dtype,
+                  int64_t w_layer_stride, int64_t bias_layer_stride, int n_layers, int batch, int embed_dim,
+                  int heads, float tau, float* scores, int32_t* branch, cudaStream_t stream) {
+  if (n_layers == 0 || batch == 0) return VB_OK;
+  dim3 grid(n_layers, batch);
+  const size_t smem = (static_cast<size_t>(embed_dim) + 3 * heads) * sizeof(float);
+  VB_REQUIRE(smem <= 48 * 1024, VB_ERR_UNSUPPORTED, "router: embedding dim %d too large", embed_dim);
+#define VB_ROUTER_LAUNCH(TE, TW)                                                                            \
+  vb_router_kernel<TE, TW><<<grid, 256, smem, stream>>>(static_cast<const TE*>(temb), static_cast<const TW*>(w), \
+                                                        static_cast<const TW*>(bias), w_layer_stride,       \
+                                                        bias_layer_stride, embed_dim, heads, tau, scores, branch)
+  if (temb_dtype == VB_DTYPE_F32 && w_dtype == VB_DTYPE_F32) VB_ROUTER_LAUNCH(float, float);
+  else if (temb_dtype == VB_DTYPE_BF16 && w_dtype == VB_DTYPE_BF16) VB_ROUTER_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (temb_dtype == VB_DTYPE_F32 && w_dtype == VB_DTYPE_BF16) VB_ROUTER_LAUNCH(float, __nv_bfloat16);
+  else if (temb_dtype == VB_DTYPE_BF16 && w_dtype == VB_DTYPE_F32) VB_ROUTER_LAUNCH(__nv_bfloat16, float);
+  else VB_REQUIRE(false, VB_ERR_INVALID, "router: unknown dtype codes %d / %d", temb_dtype, w_dtype);
+#undef VB_ROUTER_LAUNCH
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ulysses head pack / unpack (reference: vorta/ulysses/utils.py:60-74 and :84-89 transposes)
+//   pack  : x (S_loc, H, 128) -> send (P, S_loc, H/P, 128)
+//   unpack: recv (P, S_loc, H/P, 128) -> y (S_loc, H, 128)
+// Both are a permutation of 256-byte head rows; one half-warp per row, 16-byte vectors.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vb_ulysses_permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int s_loc, int heads, int world,
+                          int n_tensors, int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack) {
+  const int hp = heads / world;
+  const int64_t rows = static_cast<int64_t>(s_loc) * heads;
+  const int64_t total = rows * n_tensors * 16;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 15);
+    int64_t r = i >> 4;
+    const int t = static_cast<int>(r / rows);
+    r %= rows;
+    // r indexes the token-major side: (s, h)
+    const int h = static_cast<int>(r % heads);
+    const int64_t s = r / heads;
+    const int64_t tm = (s * heads + h) * 16 + c;                                   // (S_loc, H, 128)
+    const int64_t pm = ((static_cast<int64_t>(h / hp) * s_loc + s) * hp + (h % hp)) * 16 + c;  // (P, S_loc, H/P, 128)
+    if (pack) dst[t * (dst_tensor_stride >> 3) + pm] = src[t * (src_tensor_stride >> 3) + tm];
+    else dst[t * (dst_tensor_stride >> 3) + tm] = src[t * (src_tensor_stride >> 3) + pm];
+  }
+}
+
+int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
+                           int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream) {
+  VB_REQUIRE(world > 0 && heads % world == 0, VB_ERR_INVALID, "heads %d not divisible by world %d", heads, world);
+  VB_REQUIRE(src_tensor_stride % 8 == 0 && dst_tensor_stride % 8 == 0, VB_ERR_INVALID,
+             "tensor strides must be multiples of 8 elements");
+  const int64_t total = static_cast<int64_t>(s_loc) * heads * n_tensors * 16;
+  if (total == 0) return VB_OK;
+  const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  vb_ulysses_permute_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst),
+                                                      s_loc, heads, world, n_tensors, src_tensor_stride,
+                                                      dst_tensor_stride, pack);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb
