@@ -120,6 +120,14 @@ int vb_coreset_select(const vb_plan* plan, const void* x, int64_t stride_b, int6
                       int32_t batch, int32_t heads, int64_t* unpooled_argsort, int64_t* pooled_argsort,
                       int32_t* kept_tok, int32_t* dropped_tok, vb_stream_t stream);
 
+/* Token tables from a MatchingResults pair (the index arithmetic of unpool_sequence_by_similarity,
+ * coreset_select.py:159-166).  Inputs are the int64 argsort tables; outputs (any may be NULL):
+ *   kept_tok (B, H, S_c + text_len), dropped_tok (B, H, G, n_pooled) as in vb_coreset_select, and
+ *   unpool_src (B, H, S) int32: pooled-sequence row whose output every raster token receives. */
+int vb_coreset_tables(const vb_plan* plan, const int64_t* unpooled_argsort, const int64_t* pooled_argsort,
+                      int32_t batch, int32_t heads, int32_t* kept_tok, int32_t* dropped_tok, int32_t* unpool_src,
+                      vb_stream_t stream);
+
 /* Row gather: dst[b, h, i, :] = src[b, h, map[b, h, i], :] for i < n_rows (128 bf16 per row, 16-byte vectors).
  * replaces the index/gather/cat of pool_sequence_by_similarity (coreset_select.py:91-93,118-123) and
  * tile_layout (tile.py:7-41).  map strides of 0 share one map across heads / batches. */
@@ -166,6 +174,13 @@ typedef struct {
 int64_t vb_attn_workspace_bytes(const vb_plan* plan, int32_t batch, int32_t heads);
 int vb_attn_fwd(vb_plan* plan, const vb_attn_args* args, vb_stream_t stream);
 
+/* Dense softmax(Q K^T / sqrt(128)) V with independent query / key lengths: the base processor
+ * (WanAttnProcessor2_0._attn, wan.py:142-144: cross attention, I2V image keys, use_original_attn).  Same kernel,
+ * one key run [0, n_k).  q, out: (B, H, n_q, 128); k, v: (B, H, n_k, 128); element strides (batch, head, token). */
+int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const int64_t* q_stride,
+                  const int64_t* k_stride, const int64_t* v_stride, const int64_t* out_stride, int32_t batch,
+                  int32_t heads, int32_t n_q, int32_t n_k, vb_stream_t stream);
+
 /* Counters for bench.py: number of kernels this library launched on the calling thread since the last reset,
  * and the algorithmic attention FLOPs (BASELINE.md section 3 formulas) they covered. */
 void vb_stats_reset(void);
@@ -182,6 +197,10 @@ double vb_stats_attn_flops(void);
  * ---------------------------------------------------------------------------------------------------- */
 int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t heads, int32_t world, int32_t n_tensors,
                           int64_t x_tensor_stride, int64_t send_tensor_stride, vb_stream_t stream);
+/* q, k, v: (S_loc, H, 128) with element strides (token, head) -> send (3, P, S_loc, H/P, 128) in one pass (the
+ * reference makes two transposed copies per tensor, ulysses/utils.py:68-74,89). */
+int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h, void* send,
+                        int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream);
 int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
                             vb_stream_t stream);
 

@@ -1,0 +1,113 @@
+"""Plan tables built by the C library (host integer code) against the golden vectors and the oracle — CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vorta_oracle as O
+from vorta_b200 import _lib as L
+from vorta_b200 import ops
+from vorta_b200.attention import create_sliding_tile_attn_mask_func, get_group_info
+from vorta_b200.patch import prepare_hunyuan_self_attn_kwargs, prepare_wan_self_attn_kwargs, wan_pixel2token
+
+
+def test_group_tables_bit_exact(golden):
+    for rec in golden("group_info.pt"):
+        info = get_group_info(rec["latent"], rec["window"], rec["rate"])
+        assert info.num_unpooled_tokens_per_group == rec["n_unpooled"]
+        assert info.center_indices.dtype == torch.int64 and info.margin_indices.dtype == torch.int64
+        assert (tuple(info.center_indices.shape), tuple(info.margin_indices.shape)) == rec["shape"]
+        assert int(info.center_indices.sum()) == rec["center_sum"]
+        assert int(info.margin_indices.sum()) == rec["margin_sum"]
+        assert torch.equal(info.center_indices[:16], rec["center_head"])
+        assert torch.equal(info.margin_indices[-4:], rec["margin_tail"])
+        if rec["center"] is not None:
+            assert torch.equal(info.center_indices, rec["center"])
+            assert torch.equal(info.margin_indices, rec["margin"])
+
+
+def _mask_from_plan(plan, lat, tile, tl, tv):
+    """Expand the plan's run tables back to a dense tile-major mask (test-side only)."""
+    S = plan.seq_len
+    tau = plan.tile_tokens
+    runs = plan.export(L.EXPORT_SLIDING_RUNS).reshape(-1, 2)
+    wins = plan.export(L.EXPORT_TILE_WINDOW).reshape(-1, 6)
+    nt = [lat[d] // tile[d] for d in range(3)]
+    n = S + tl
+    mask = torch.zeros(n, n, dtype=torch.bool)
+    for t in range(wins.shape[0]):
+        lo, hi = wins[t, :3], wins[t, 3:]
+        for a in range(lo[0], hi[0] + 1):
+            for b in range(lo[1], hi[1] + 1):
+                k0 = ((a * nt[1] + b) * nt[2] + lo[2]) * tau
+                k1 = ((a * nt[1] + b) * nt[2] + hi[2] + 1) * tau
+                mask[t * tau:(t + 1) * tau, k0:k1] = True
+        mask[t * tau:(t + 1) * tau, S:S + tv] = True
+    mask[S:S + tv, :S + tv] = True
+    return mask, runs
+
+
+def test_sliding_schedule_equals_reference_mask(golden):
+    for rec in golden("tile_mask.pt"):
+        lat, win, tile, tl, tv = rec["latent"], rec["window"], rec["tile"], rec["text_len"], rec["text_valid"]
+        plan = ops.Plan(lat, tile, win, (1, 1, 1), n_unpooled=0, text_len=tl, text_valid=tv)
+        tile_map = plan.export(L.EXPORT_TILE_MAP)
+        assert np.array_equal(tile_map[:plan.seq_len], rec["tile_perm"].numpy())
+        assert np.array_equal(tile_map[plan.seq_len:], np.arange(plan.seq_len, plan.seq_len + tl))
+        mask, runs = _mask_from_plan(plan, lat, tile, tl, tv)
+        n = mask.shape[0]
+        ref = torch.from_numpy(np.unpackbits(rec["mask_bits"].numpy())[:n * n].reshape(n, n).astype(bool))
+        assert torch.equal(mask, ref)
+        assert plan.query(L.PLAN_KEYS_PER_QUERY) + tv == rec["keys_q0"]
+        assert np.array_equal(plan.export(L.EXPORT_TILE_WINDOW).reshape(-1, 6), O.tile_windows(lat, win, tile))
+        # the run table covers exactly the allowed keys of every query tile
+        assert (runs[:, 1] > 0).all()
+
+
+def test_run_table_expands_to_mask_rows():
+    lat, win, tile = (4, 8, 12), (3, 3, 3), (2, 4, 4)
+    plan = ops.Plan(lat, tile, win, (1, 1, 1), n_unpooled=0)
+    runs = plan.export(L.EXPORT_SLIDING_RUNS).reshape(-1, 2)
+    mask = O.sliding_tile_mask(lat, win, tile)
+    tau = plan.tile_tokens
+    # tiles appear in order, each with its own consecutive group of runs whose union is the mask row
+    idx = 0
+    for t in range(plan.num_tiles):
+        row = mask[t * tau]
+        want = int(row.sum())
+        got = torch.zeros_like(row)
+        while want > int(got.sum()):
+            s, n = runs[idx]
+            assert not got[s:s + n].any()
+            got[s:s + n] = True
+            idx += 1
+        assert torch.equal(got, row)
+    assert idx == runs.shape[0]
+
+
+def test_baseline_shapes_build():
+    # BASELINE.json grids with the substitute hyper-parameters of SURVEY.md section 8d
+    for lat, tile, lw in [((21, 30, 52), (3, 10, 4), (3, 3, 2)), ((21, 45, 80), (3, 9, 16), (3, 3, 2)),
+                          ((20, 45, 80), (5, 9, 8), (2, 3, 2)), ((33, 45, 80), (3, 9, 16), (3, 3, 2))]:
+        plan = ops.Plan(lat, tile, (3, 3, 3), lw, 0.5)
+        S = lat[0] * lat[1] * lat[2]
+        assert plan.seq_len == S and plan.coreset_len == S // 2
+        assert plan.query(L.PLAN_KEYS_PER_QUERY) == 27 * plan.tile_tokens
+        for e in range(3):
+            ref = O.branch_flops(e, lat, (3, 3, 3), tile, lw, 0.5)
+            assert abs(plan.flops_per_head(e) - ref) / ref < 1e-12
+
+
+def test_prepare_kwargs_mirror_reference_keys():
+    kw = dict(latent_shape=(4, 6, 8), window_size=(3, 3, 3), tile_size=(2, 3, 4), lowres_window_size=(2, 3, 2),
+              lowres_reduction_rate=0.5)
+    out = prepare_wan_self_attn_kwargs(dict(kw), torch.device("cpu"), tau_sparse=0.3)
+    assert set(out) == {"latent_shape", "window_size", "tile_size", "lowres_group_info", "flex_attn_mask_func",
+                        "tau_sparse"}
+    out = prepare_hunyuan_self_attn_kwargs(dict(kw), torch.device("cpu"))
+    assert set(out) == {"latent_shape", "window_size", "tile_size", "lowres_group_info"}
+    assert wan_pixel2token((77, 720, 1280)) == (20, 45, 80)
+    assert wan_pixel2token((81, 480, 832)) == (21, 30, 52)
+    with pytest.raises(ValueError):
+        wan_pixel2token((78, 720, 1280))
+    sched = create_sliding_tile_attn_mask_func((4, 6, 8), (3, 3, 3), (2, 3, 4), 0, 0)
+    assert sched.tile_windows().shape == (8, 6)

@@ -33,10 +33,10 @@ EXPORT_CENTER_INDICES, EXPORT_MARGIN_INDICES, EXPORT_TILE_MAP, EXPORT_TILE_WINDO
 EXPORTED_SYMBOLS = (
     "vb_last_error", "vb_version", "vb_device_check",
     "vb_plan_create", "vb_plan_destroy", "vb_plan_set_text_valid", "vb_plan_query", "vb_plan_export",
-    "vb_router_forward", "vb_coreset_select", "vb_gather_rows",
-    "vb_attn_workspace_bytes", "vb_attn_fwd",
+    "vb_router_forward", "vb_coreset_select", "vb_coreset_tables", "vb_gather_rows",
+    "vb_attn_workspace_bytes", "vb_attn_fwd", "vb_attn_dense",
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops",
-    "vb_ulysses_pack_heads", "vb_ulysses_unpack_heads",
+    "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_unpack_heads",
 )
 
 
@@ -105,6 +105,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_router_forward.argtypes = [vp, C.c_int, vp, vp, C.c_int, i64, i64, i32, i32, i32, i32, f32, vp, vp, vp]
     lib.vb_coreset_select.restype = C.c_int
     lib.vb_coreset_select.argtypes = [vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp]
+    lib.vb_coreset_tables.restype = C.c_int
+    lib.vb_coreset_tables.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.vb_attn_dense.restype = C.c_int
+    lib.vb_attn_dense.argtypes = [vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                                  i32, i32, i32, i32, vp]
     lib.vb_gather_rows.restype = C.c_int
     lib.vb_gather_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, vp]
     lib.vb_attn_workspace_bytes.restype = i64
@@ -116,6 +121,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_stats_attn_flops.restype = C.c_double
     lib.vb_ulysses_pack_heads.restype = C.c_int
     lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp]
+    lib.vb_ulysses_pack_qkv.restype = C.c_int
+    lib.vb_ulysses_pack_qkv.argtypes = [vp, vp, vp, i64, i64, vp, i32, i32, i32, vp]
     lib.vb_ulysses_unpack_heads.restype = C.c_int
     lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, vp]
 

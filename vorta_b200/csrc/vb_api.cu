@@ -27,6 +27,7 @@ static thread_local double g_flops = 0.0;
 // ---- kernels implemented in the other translation units -----------------------------------------
 int launch_coreset_select(const SelectParams& p, cudaStream_t stream);
 int launch_gather_rows(const GatherParams& p, cudaStream_t stream);
+int launch_coreset_tables(const TablesParams& p, cudaStream_t stream);
 int launch_zero_rows(__nv_bfloat16* out, int64_t sb, int64_t sh, int64_t ss, int batch, int heads, int row0,
                      int n_rows, cudaStream_t stream);
 int launch_router(const void* temb, int temb_dtype, const void* w, const void* bias, int w_dtype,
@@ -34,6 +35,8 @@ int launch_router(const void* temb, int temb_dtype, const void* w, const void* b
                   int heads, float tau, float* scores, int32_t* branch, cudaStream_t stream);
 int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
                            int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream);
+int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h,
+                            void* send, int s_loc, int heads, int world, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
@@ -414,6 +417,22 @@ int vb_coreset_select(const vb_plan* pl, const void* x, int64_t stride_b, int64_
   return rc;
 }
 
+int vb_coreset_tables(const vb_plan* pl, const int64_t* unpooled_argsort, const int64_t* pooled_argsort,
+                      int32_t batch, int32_t heads, int32_t* kept_tok, int32_t* dropped_tok, int32_t* unpool_src,
+                      vb_stream_t stream) {
+  VB_REQUIRE(pl && unpooled_argsort && pooled_argsort, VB_ERR_INVALID, "null argument");
+  VB_REQUIRE(pl->has_device, VB_ERR_UNSUPPORTED, "no CUDA device: vorta_b200 has no CPU path");
+  TablesParams p;
+  p.unpooled_argsort = unpooled_argsort; p.pooled_argsort = pooled_argsort;
+  p.center_tok = pl->d_center_tok; p.margin_tok = pl->d_margin_tok;
+  p.batch = batch; p.heads = heads; p.G = pl->G; p.n_margin = pl->g - 1; p.n_unpooled = pl->n_u;
+  p.seq_len = pl->S; p.text_len = pl->d.text_len;
+  p.kept_tok = kept_tok; p.dropped_tok = dropped_tok; p.unpool_src = unpool_src;
+  int rc = launch_coreset_tables(p, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+
 int vb_gather_rows(const void* src, int64_t src_stride_b, int64_t src_stride_h, int64_t src_stride_s, void* dst,
                    int64_t dst_stride_b, int64_t dst_stride_h, int64_t dst_stride_s, const int32_t* map,
                    int64_t map_stride_b, int64_t map_stride_h, int32_t batch, int32_t heads, int32_t n_rows,
@@ -707,6 +726,44 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   return VB_OK;
 }
 
+// Dense attention with independent query / key lengths; schedules are cached per (n_q, n_k).
+int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const int64_t* q_stride,
+                  const int64_t* k_stride, const int64_t* v_stride, const int64_t* out_stride, int32_t batch,
+                  int32_t heads, int32_t n_q, int32_t n_k, vb_stream_t stream_) {
+  VB_REQUIRE(q && k && v && out && q_stride && k_stride && v_stride && out_stride, VB_ERR_INVALID, "null argument");
+  VB_REQUIRE(batch > 0 && heads > 0 && n_q > 0 && n_k > 0, VB_ERR_INVALID, "sizes must be positive");
+  static thread_local std::vector<std::pair<std::pair<int, int>, Schedule*>> cache;
+  Schedule* sched = nullptr;
+  for (auto& e : cache)
+    if (e.first.first == n_q && e.first.second == n_k) sched = e.second;
+  if (sched == nullptr) {
+    sched = new Schedule();
+    sched->runs.push_back({0, n_k});
+    sched->add_query_range(0, n_q, 0, 1, n_k);
+    int rc = sched->upload();
+    if (rc != VB_OK) {
+      delete sched;
+      return rc;
+    }
+    cache.push_back({{n_q, n_k}, sched});
+  }
+  vb_attn_args a;
+  memset(&a, 0, sizeof(a));
+  a.out = out; a.batch = batch; a.heads = heads;
+  for (int i = 0; i < 3; ++i) a.out_stride[i] = out_stride[i];
+  BranchLaunch bl;
+  memset(&bl, 0, sizeof(bl));
+  bl.q = static_cast<const __nv_bfloat16*>(q);
+  bl.k = static_cast<const __nv_bfloat16*>(k);
+  bl.v = static_cast<const __nv_bfloat16*>(v);
+  for (int i = 0; i < 3; ++i) { bl.qs[i] = q_stride[i]; bl.ks[i] = k_stride[i]; bl.vs[i] = v_stride[i]; }
+  bl.n_rows_q = n_q; bl.n_rows_kv = n_k; bl.n_heads_tensor = heads;
+  bl.sched = sched;
+  std::vector<AttnHead> hs(heads);
+  for (int h = 0; h < heads; ++h) hs[h] = AttnHead{h, h, 1.f, 0};
+  return run_branch(bl, a, hs, 0, batch, static_cast<cudaStream_t>(stream_));
+}
+
 void vb_stats_reset(void) {
   g_launches = 0;
   g_flops = 0.0;
@@ -719,6 +776,14 @@ int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t head
   VB_REQUIRE(x && send, VB_ERR_INVALID, "null argument");
   int rc = launch_ulysses_permute(x, send, s_loc, heads, world, n_tensors, x_tensor_stride, send_tensor_stride, 1,
                                   static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h, void* send,
+                        int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream) {
+  VB_REQUIRE(q && k && v && send, VB_ERR_INVALID, "null argument");
+  int rc = launch_ulysses_pack_qkv(q, k, v, stride_s, stride_h, send, s_loc, heads, world,
+                                   static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }

@@ -90,6 +90,17 @@ struct SelectParams {
   int32_t* kept_tok;           // (B, heads, S_c + text_len)
   int32_t* dropped_tok;        // (B, heads, G, n_margin - n_u)
 };
+// Token tables from int64 matching tables (vb_kernels.cu)
+struct TablesParams {
+  const int64_t* unpooled_argsort;
+  const int64_t* pooled_argsort;
+  const int32_t* center_tok;
+  const int32_t* margin_tok;
+  int32_t batch, heads, G, n_margin, n_unpooled, seq_len, text_len;
+  int32_t* kept_tok;
+  int32_t* dropped_tok;
+  int32_t* unpool_src;
+};
 // Row gather launch parameters: up to three tensors share one row map (vb_kernels.cu)
 struct GatherParams {
   const __nv_bfloat16* src[3];

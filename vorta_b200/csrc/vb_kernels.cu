@@ -118,6 +118,54 @@ int launch_coreset_select(const SelectParams& p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Matching tables -> token tables (reference: coreset_select.py:157-166), one thread per (b, h, group, margin)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vb_coreset_tables_kernel(const TablesParams p) {
+  const int n_p = p.n_margin - p.n_unpooled;
+  const int S_c = p.G * (1 + p.n_unpooled);
+  const int row_len = S_c + p.text_len;
+  const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G * (p.n_margin + 1);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % (p.n_margin + 1));      // 0 = centre, 1.. = sorted margin rank j-1
+    const int64_t u = i / (p.n_margin + 1);
+    const int grp = static_cast<int>(u % p.G);
+    const int64_t bh = u / p.G;
+    if (j == 0) {
+      const int tok = p.center_tok[grp];
+      if (p.kept_tok) p.kept_tok[bh * row_len + grp] = tok;
+      if (p.unpool_src) p.unpool_src[bh * p.seq_len + tok] = grp;
+      if (p.kept_tok && grp == 0)
+        for (int t = 0; t < p.text_len; ++t) p.kept_tok[bh * row_len + S_c + t] = p.seq_len + t;
+      continue;
+    }
+    const int rank = j - 1;
+    if (rank < p.n_unpooled) {
+      const int pos = static_cast<int>(p.unpooled_argsort[(bh * p.G + grp) * p.n_unpooled + rank]);
+      const int tok = p.margin_tok[static_cast<int64_t>(grp) * p.n_margin + pos];
+      const int row = p.G + grp * p.n_unpooled + rank;
+      if (p.kept_tok) p.kept_tok[bh * row_len + row] = tok;
+      if (p.unpool_src) p.unpool_src[bh * p.seq_len + tok] = row;
+    } else {
+      const int r = rank - p.n_unpooled;
+      const int pos = static_cast<int>(p.pooled_argsort[(bh * p.G + grp) * n_p + r]);
+      const int tok = p.margin_tok[static_cast<int64_t>(grp) * p.n_margin + pos];
+      if (p.dropped_tok) p.dropped_tok[(bh * p.G + grp) * n_p + r] = tok;
+      if (p.unpool_src) p.unpool_src[bh * p.seq_len + tok] = grp;   // dropped margins copy their centre
+    }
+  }
+}
+
+int launch_coreset_tables(const TablesParams& p, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G * (p.n_margin + 1);
+  if (total == 0) return VB_OK;
+  const int grid = static_cast<int>((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  vb_coreset_tables_kernel<<<grid, 256, 0, stream>>>(p);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row gather: dst[t][b, hs, i, :] = src[t][b, head_list[hs], map[b, hs, i], :], up to 3 tensors per launch
 // (reference: coreset_select.py:91-93,118-123 pooling; tile.py:7-41 tile-major layout)
 // ------------------------------------------------------------------------------------------------
@@ -296,6 +344,43 @@ vb_ulysses_permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst
     if (pack) dst[t * (dst_tensor_stride >> 3) + pm] = src[t * (src_tensor_stride >> 3) + tm];
     else dst[t * (dst_tensor_stride >> 3) + tm] = src[t * (src_tensor_stride >> 3) + pm];
   }
+}
+
+// q, k, v (S_loc, H, 128) with (token, head) strides -> send (3, P, S_loc, H/P, 128) in ONE pass; each tensor's
+// (P, S_loc, H/P, 128) block is the send buffer of one equal-split all-to-all.
+__global__ void __launch_bounds__(256)
+vb_ulysses_pack_qkv_kernel(const uint4* __restrict__ q, const uint4* __restrict__ k, const uint4* __restrict__ v,
+                           int64_t stride_s, int64_t stride_h, uint4* __restrict__ send, int s_loc, int heads,
+                           int world) {
+  const int hp = heads / world;
+  const int64_t rows = static_cast<int64_t>(s_loc) * heads;
+  const int64_t total = rows * 3 * 16;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 15);
+    int64_t r = i >> 4;
+    const int t = static_cast<int>(r / rows);
+    r %= rows;
+    const int h = static_cast<int>(r % heads);
+    const int64_t s = r / heads;
+    const uint4* src = t == 0 ? q : (t == 1 ? k : v);
+    const int64_t dst = ((((static_cast<int64_t>(t) * world + h / hp) * s_loc + s) * hp) + (h % hp)) * 16 + c;
+    send[dst] = src[(s * stride_s + h * stride_h) / 8 + c];
+  }
+}
+
+int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h,
+                            void* send, int s_loc, int heads, int world, cudaStream_t stream) {
+  VB_REQUIRE(world > 0 && heads % world == 0, VB_ERR_INVALID, "heads %d not divisible by world %d", heads, world);
+  VB_REQUIRE(stride_s % 8 == 0 && stride_h % 8 == 0, VB_ERR_INVALID, "strides must be multiples of 8 elements");
+  const int64_t total = static_cast<int64_t>(s_loc) * heads * 3 * 16;
+  if (total == 0) return VB_OK;
+  const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  vb_ulysses_pack_qkv_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(q), static_cast<const uint4*>(k),
+                                                       static_cast<const uint4*>(v), stride_s, stride_h,
+                                                       static_cast<uint4*>(send), s_loc, heads, world);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
 }
 
 int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,

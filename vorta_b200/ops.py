@@ -250,3 +250,37 @@ def stats_reset() -> None:
 def stats() -> Tuple[int, float]:
     lib = L.lib()
     return int(lib.vb_stats_launches()), float(lib.vb_stats_attn_flops())
+
+
+def coreset_tables(plan: Plan, unpooled_argsort: torch.Tensor, pooled_argsort: torch.Tensor):
+    """(kept_tok, dropped_tok, unpool_src) int32 token tables from a MatchingResults pair
+    (the index arithmetic of coreset_select.py:159-166)."""
+    if not unpooled_argsort.is_cuda:
+        raise L.VortaB200Error("coreset_tables needs CUDA tensors: vorta_b200 has no CPU path")
+    un = unpooled_argsort.to(torch.int64).contiguous()
+    po = pooled_argsort.to(torch.int64).contiguous()
+    B, H = un.shape[:2]
+    dev = un.device
+    kept = torch.empty((B, H, plan.coreset_len + plan.text_len), dtype=torch.int32, device=dev)
+    drop = torch.empty((B, H, plan.num_groups, max(plan.num_pooled, 1)), dtype=torch.int32, device=dev)
+    src = torch.empty((B, H, plan.seq_len), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().vb_coreset_tables(plan.handle, un.data_ptr(), po.data_ptr(), B, H, kept.data_ptr(),
+                                          drop.data_ptr(), src.data_ptr(), _stream_ptr(dev)))
+    return kept, drop[..., :plan.num_pooled], src
+
+
+def attn_dense(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(128)) V with independent query / key lengths (wan.py:142-144), (B, H, N, 128) views."""
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _require_cuda_bf16(name, t)
+    B, H, Nq, D = q.shape
+    Nk = k.shape[2]
+    if out is None:
+        out = torch.empty((B, Nq, H, D), dtype=q.dtype, device=q.device).transpose(1, 2)
+    i64x3 = C.c_int64 * 3
+    with torch.cuda.device(q.device):
+        L.check(L.lib().vb_attn_dense(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                      i64x3(*q.stride()[:3]), i64x3(*k.stride()[:3]), i64x3(*v.stride()[:3]),
+                                      i64x3(*out.stride()[:3]), B, H, Nq, Nk, _stream_ptr(q.device)))
+    return out
