@@ -187,6 +187,12 @@ void vb_stats_reset(void);
 int64_t vb_stats_launches(void);
 double vb_stats_attn_flops(void);
 
+/* Live timing of the attention kernel for the roofline line of bench.py: while enabled, every launch of the
+ * tcgen05 attention kernel is bracketed by CUDA events on its own stream; vb_timing_collect waits for them and
+ * returns the summed kernel time (ms), the number of launches and their algorithmic FLOPs, then clears. */
+void vb_timing_enable(int on);
+int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops);
+
 /* ------------------------------------------------------------------------------------------------------
  * Ulysses sequence parallelism helpers (vorta/ulysses/utils.py:15-93).  The exchange itself is an NCCL
  * all-to-all issued by the host through torch.distributed; these kernels produce / consume its buffers.

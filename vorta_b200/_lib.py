@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     "vb_plan_create", "vb_plan_destroy", "vb_plan_set_text_valid", "vb_plan_query", "vb_plan_export",
     "vb_router_forward", "vb_coreset_select", "vb_coreset_tables", "vb_gather_rows",
     "vb_attn_workspace_bytes", "vb_attn_fwd", "vb_attn_dense",
-    "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops",
+    "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
     "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_unpack_heads",
 )
 
@@ -119,6 +119,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_stats_reset.restype = None
     lib.vb_stats_launches.restype = i64
     lib.vb_stats_attn_flops.restype = C.c_double
+    lib.vb_timing_enable.restype = None
+    lib.vb_timing_enable.argtypes = [C.c_int]
+    lib.vb_timing_collect.restype = C.c_int
+    lib.vb_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb_ulysses_pack_heads.restype = C.c_int
     lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp]
     lib.vb_ulysses_pack_qkv.restype = C.c_int

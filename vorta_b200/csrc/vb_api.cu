@@ -23,6 +23,10 @@ const char* get_error() { return g_err; }
 
 static thread_local int64_t g_launches = 0;
 static thread_local double g_flops = 0.0;
+// optional live timing of the attention kernel (bench.py roofline): event pairs on the launching stream
+static thread_local bool g_timing = false;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+static thread_local double g_timed_flops = 0.0;
 
 // ---- kernels implemented in the other translation units -----------------------------------------
 int launch_coreset_select(const SelectParams& p, cudaStream_t stream);
@@ -525,8 +529,19 @@ static int run_branch(const BranchLaunch& bl, const vb_attn_args& a, const std::
     const int n = static_cast<int>(std::min<size_t>(kMaxHeads, heads.size() - h0));
     p.n_heads = n;
     for (int i = 0; i < n; ++i) p.heads[i] = heads[h0 + i];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_timing) {
+      VB_CUDA_OK(cudaEventCreate(&ev0));
+      VB_CUDA_OK(cudaEventCreate(&ev1));
+      VB_CUDA_OK(cudaEventRecord(ev0, stream));
+    }
     rc = launch_attn(mq, mk, mv, p, static_cast<int>(bl.sched->pairs.size()), n, nbatch, stream);
     if (rc != VB_OK) return rc;
+    if (g_timing) {
+      VB_CUDA_OK(cudaEventRecord(ev1, stream));
+      g_events.push_back({ev0, ev1});
+      g_timed_flops += bl.sched->flops_per_head * n * nbatch;
+    }
     ++g_launches;
     g_flops += bl.sched->flops_per_head * n * nbatch;
   }
@@ -762,6 +777,26 @@ int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const 
   std::vector<AttnHead> hs(heads);
   for (int h = 0; h < heads; ++h) hs[h] = AttnHead{h, h, 1.f, 0};
   return run_branch(bl, a, hs, 0, batch, static_cast<cudaStream_t>(stream_));
+}
+
+void vb_timing_enable(int on) { g_timing = on != 0; }
+
+int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops) {
+  double total = 0.0;
+  for (auto& e : g_events) {
+    VB_CUDA_OK(cudaEventSynchronize(e.second));
+    float ms = 0.f;
+    VB_CUDA_OK(cudaEventElapsedTime(&ms, e.first, e.second));
+    total += ms;
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  if (kernel_ms) *kernel_ms = total;
+  if (launches) *launches = static_cast<int64_t>(g_events.size());
+  if (flops) *flops = g_timed_flops;
+  g_events.clear();
+  g_timed_flops = 0.0;
+  return VB_OK;
 }
 
 void vb_stats_reset(void) {

@@ -284,3 +284,14 @@ def attn_dense(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[
                                       i64x3(*q.stride()[:3]), i64x3(*k.stride()[:3]), i64x3(*v.stride()[:3]),
                                       i64x3(*out.stride()[:3]), B, H, Nq, Nk, _stream_ptr(q.device)))
     return out
+
+
+def timing_enable(on: bool) -> None:
+    L.lib().vb_timing_enable(1 if on else 0)
+
+
+def timing_collect() -> Tuple[float, int, float]:
+    """(summed attention-kernel ms, launches, algorithmic FLOPs) since the last collect; waits for the events."""
+    ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+    L.check(L.lib().vb_timing_collect(C.byref(ms), C.byref(n), C.byref(fl)))
+    return float(ms.value), int(n.value), float(fl.value)

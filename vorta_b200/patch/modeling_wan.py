@@ -1,0 +1,156 @@
+"""Install boundary for Wan — the reference's ``vorta/patch/modeling_wan.py`` (apply_vorta_transformer :265-310,
+wan_block_routed_forward :195-239, wan_transformer_3d_routed_forward :38-192, wan_rope_forward :242-262).
+
+Works on any model with the Wan module tree (diffusers' WanTransformer3DModel or ``vorta_b200.dit.WanDiT``).
+Differences from the reference, by design:
+* the routers of ALL blocks are evaluated in one launch at the start of the forward (they only read ``temb``,
+  modeling_wan.py:215) and their top-1 decisions reach the host in one copy, instead of one sync per block;
+* under Ulysses the sequence is sharded by TOKENS inside the forward (the reference shards frames in the
+  pipeline, pipeline_wan.py:120-122), and the RoPE table is narrowed per rank in the processor (wan.py:97);
+* the router-training losses of the reference forward (reg / distillation) are out of scope.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, Optional
+
+import torch
+
+from ..attention import WanAttnProcessor2_0, WanAttnProcessorTripleEval, WanAttnProcessorTripleTrain
+from ..ulysses import SP_STATE, all_gather
+from .router import Router, route_step
+
+
+def wan_rope_forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+    """(1, 1, T*H*W, D/2) complex phases for the FULL token grid (modeling_wan.py:242-262); every rank builds the
+    whole table and the processor narrows it to its token shard."""
+    _, _, num_frames, height, width = hidden_states.shape
+    p_t, p_h, p_w = self.patch_size
+    ppf, pph, ppw = num_frames // p_t, height // p_h, width // p_w
+    d = self.attention_head_dim
+    freqs = self.freqs.to(hidden_states.device).split_with_sizes([d // 2 - 2 * (d // 6), d // 6, d // 6], dim=1)
+    f = freqs[0][:ppf].view(ppf, 1, 1, -1).expand(ppf, pph, ppw, -1)
+    h = freqs[1][:pph].view(1, pph, 1, -1).expand(ppf, pph, ppw, -1)
+    w = freqs[2][:ppw].view(1, 1, ppw, -1).expand(ppf, pph, ppw, -1)
+    return torch.cat([f, h, w], dim=-1).reshape(1, 1, ppf * pph * ppw, -1)
+
+
+def wan_block_routed_forward(self, hidden_states, encoder_hidden_states, temb, rotary_emb,
+                             temb_before_proj: Optional[torch.Tensor], use_original_attn: bool = False,
+                             self_attention_kwargs: Optional[Dict[str, Any]] = None,
+                             routing_score: Optional[torch.Tensor] = None, branch=None):
+    """Dataflow of modeling_wan.py:195-239.  ``routing_score`` / ``branch`` may be supplied by the caller when the
+    step's routing was precomputed; otherwise the block's router runs here like in the reference."""
+    shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = (
+        self.scale_shift_table + temb.float()).chunk(6, dim=1)
+
+    norm_hidden_states = (self.norm1(hidden_states.float()) * (1 + scale_msa) + shift_msa).type_as(hidden_states)
+    if not use_original_attn and routing_score is None:
+        routing_score = self.router(temb_before_proj)
+    kwargs = dict(self_attention_kwargs or {})
+    if branch is not None:
+        kwargs["branch"] = branch
+    attn_output = self.attn1(hidden_states=norm_hidden_states, rotary_emb=rotary_emb, routing_score=routing_score,
+                             use_original_attn=use_original_attn, **kwargs)
+    hidden_states = (hidden_states.float() + attn_output * gate_msa).type_as(hidden_states)
+
+    norm_hidden_states = self.norm2(hidden_states.float()).type_as(hidden_states)
+    attn_output = self.attn2(hidden_states=norm_hidden_states, encoder_hidden_states=encoder_hidden_states)
+    hidden_states = hidden_states + attn_output
+
+    norm_hidden_states = (self.norm3(hidden_states.float()) * (1 + c_scale_msa) + c_shift_msa).type_as(hidden_states)
+    ff_output = self.ffn(norm_hidden_states)
+    hidden_states = (hidden_states.float() + ff_output.float() * c_gate_msa).type_as(hidden_states)
+    return hidden_states, routing_score
+
+
+def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor,
+                                      encoder_hidden_states: torch.Tensor,
+                                      encoder_hidden_states_image: Optional[torch.Tensor] = None,
+                                      return_dict: bool = False, attention_kwargs=None,
+                                      self_attention_kwargs: Optional[Dict[str, Any]] = None,
+                                      return_routing_scores: bool = False):
+    """One DiT forward = one denoise step (dataflow of modeling_wan.py:38-192 without the training losses)."""
+    batch_size, _, num_frames, height, width = hidden_states.shape
+    p_t, p_h, p_w = self.config.patch_size
+    ppf, pph, ppw = num_frames // p_t, height // p_h, width // p_w
+
+    rotary_emb = self.rope(hidden_states)
+    hidden_states = self.patch_embedding(hidden_states).flatten(2).transpose(1, 2)
+    temb, timestep_proj, encoder_hidden_states, _ = self.condition_embedder(
+        timestep, encoder_hidden_states, encoder_hidden_states_image)
+    timestep_proj = timestep_proj.unflatten(1, (6, -1))
+
+    if SP_STATE.enabled:        # token sharding: S / P contiguous tokens per rank
+        s_loc = hidden_states.shape[1] // SP_STATE.sp_size
+        hidden_states = hidden_states.narrow(1, SP_STATE.group_local_rank * s_loc, s_loc).contiguous()
+
+    kwargs = dict(self_attention_kwargs or {})
+    tau = kwargs.get("tau_sparse")
+    eval_mode = isinstance(self.blocks[0].attn1.processor, WanAttnProcessorTripleEval)
+    # routing of the whole step in one launch: it depends on temb only
+    scores, branches = route_step([b.router for b in self.blocks], temb, tau if eval_mode else None)
+    routing_scores = []
+    for i, block in enumerate(self.blocks):
+        score_i = scores[i].to(temb.dtype)
+        hidden_states, _ = block(hidden_states, encoder_hidden_states, timestep_proj, rotary_emb,
+                                 temb_before_proj=temb, use_original_attn=False, self_attention_kwargs=kwargs,
+                                 routing_score=score_i, branch=branches[i] if eval_mode else None)
+        if return_routing_scores:
+            routing_scores.append(score_i)
+
+    shift, scale = (self.scale_shift_table + temb.unsqueeze(1)).chunk(2, dim=1)
+    hidden_states = (self.norm_out(hidden_states.float()) * (1 + scale) + shift).type_as(hidden_states)
+    hidden_states = self.proj_out(hidden_states)
+    if SP_STATE.enabled:
+        hidden_states = all_gather(hidden_states, dim=1)
+    hidden_states = hidden_states.reshape(batch_size, ppf, pph, ppw, p_t, p_h, p_w, -1)
+    hidden_states = hidden_states.permute(0, 7, 1, 4, 2, 5, 3, 6)
+    output = hidden_states.flatten(6, 7).flatten(4, 5).flatten(2, 3)
+    if return_routing_scores:
+        return output, routing_scores
+    return (output,) if not return_dict else {"sample": output}
+
+
+def load_router_checkpoint(checkpoint_file: os.PathLike, model) -> None:
+    """Router-only checkpoint (reference: vorta/train/checkpoint.py:63-74): keys ``blocks.{i}.router.linear.*``."""
+    state = torch.load(checkpoint_file, map_location="cpu", weights_only=True)
+    own = model.state_dict()
+    own.update({k: v for k, v in state.items() if "router" in k})
+    model.load_state_dict(own)
+
+
+def apply_vorta_transformer(model, train_router: bool = False, checkpoint_file: Optional[os.PathLike] = None,
+                            attn_processor_kwargs: Optional[Dict[str, Any]] = None,
+                            router_dtype: Optional[torch.dtype] = None):
+    """Same signature and effect as modeling_wan.py:265-310."""
+    processor_cls = WanAttnProcessorTripleTrain if train_router else WanAttnProcessorTripleEval
+    model.__class__.forward = wan_transformer_3d_routed_forward
+    model.rope.__class__.forward = wan_rope_forward
+    param = next(model.parameters())
+    dtype = router_dtype or param.dtype
+    embedding_dim = model.condition_embedder.time_proj.in_features
+    attn_processor_kwargs = dict(attn_processor_kwargs or {})
+    attn_processor_kwargs.update(check_input=True)
+    for block in model.blocks:
+        if not hasattr(block, "router"):
+            block.router = Router(embedding_dim=embedding_dim, heads=block.attn1.heads, num_experts=3).to(
+                device=param.device, dtype=dtype)
+        if train_router:
+            block.router.requires_grad_(True)
+        block.attn1.set_processor(processor_cls(**attn_processor_kwargs))
+        block.attn2.set_processor(WanAttnProcessor2_0())
+        attn_processor_kwargs.update(check_input=False)       # only the first block checks (modeling_wan.py:303)
+        block.__class__.forward = wan_block_routed_forward
+    if checkpoint_file is not None:
+        load_router_checkpoint(checkpoint_file, model)
+    return model
+
+
+def apply_sp_flashattn_transformer(model):
+    """Baseline-only variant (modeling_wan.py:313-323): dense attention processors, no routing."""
+    model.rope.__class__.forward = wan_rope_forward
+    for block in model.blocks:
+        block.attn1.set_processor(WanAttnProcessor2_0())
+        block.attn2.set_processor(WanAttnProcessor2_0())
+    return model
