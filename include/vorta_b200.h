@@ -203,10 +203,11 @@ int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops);
  * ---------------------------------------------------------------------------------------------------- */
 int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t heads, int32_t world, int32_t n_tensors,
                           int64_t x_tensor_stride, int64_t send_tensor_stride, vb_stream_t stream);
-/* q, k, v: (S_loc, H, 128) with element strides (token, head) -> send (3, P, S_loc, H/P, 128) in one pass (the
- * reference makes two transposed copies per tensor, ulysses/utils.py:68-74,89). */
-int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h, void* send,
-                        int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream);
+/* q, k, v: (S_loc, H, 128), each with its own element strides stride_s[3] (token) / stride_h[3] (head) ->
+ * send (3, P, S_loc, H/P, 128) in one pass (the reference makes two transposed copies per tensor,
+ * ulysses/utils.py:68-74,89). */
+int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s, const int64_t* stride_h,
+                        void* send, int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream);
 int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
                             vb_stream_t stream);
 

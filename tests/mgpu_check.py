@@ -1,0 +1,91 @@
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU): the Ulysses-parallel processors must reproduce
+the single-GPU result (the N-GPU == 1-GPU contract of SURVEY.md section 5).  Prints one line per case; exits
+non-zero on a mismatch.  Driven by tests/test_multigpu.py."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import fixtures as FX  # noqa: E402
+from vorta_b200.attention import (HunyuanVideoFlashAttnProcessorTripleEval, WanAttnProcessorTripleEval,  # noqa: E402
+                                  WanAttnProcessorTripleTrain, get_group_info)
+from vorta_b200.ulysses import SP_STATE, all_gather  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+
+    def check(name, got, ref, tol=2e-2):
+        nonlocal ok
+        err = (got.float() - ref.float()).abs().max().item()
+        scale = ref.float().abs().max().item()
+        good = err <= tol * max(scale, 1.0)
+        ok &= good
+        if rank == 0:
+            print(f"{name:40s} max_abs={err:.3e} (ref absmax {scale:.3e}) {'OK' if good else 'MISMATCH'}", flush=True)
+
+    # ---------------- Wan: H = 4 * world heads so that every branch lands on every rank mix ----------------
+    lat, tile, win, lw = (4, 6, 8), (2, 3, 4), (3, 3, 3), (2, 3, 2)
+    S, H = 192, 4 * world
+    attn = FX.FakeWanAttn(H, seed=5).to(dev, torch.bfloat16)
+    hs = FX.det_tensor((1, S, H * 128), 6).to(dev, torch.bfloat16)
+    rot = FX.wan_rotary(S, 7).to(dev)
+    kw = dict(lowres_group_info=get_group_info(lat, lw, 0.5, device=dev), flex_attn_mask_func=None,
+              window_size=win, tile_size=tile, latent_shape=lat)
+    score = torch.softmax(FX.det_tensor((1, H, 3), 8, 4.0), -1).to(dev)
+    ev, tr = WanAttnProcessorTripleEval(check_input=True), WanAttnProcessorTripleTrain(check_input=True)
+    with torch.no_grad():
+        ref_eval = ev(attn, hs, None, None, rot, tau_sparse=0.3, routing_score=score, **kw)
+        ref_train = tr(attn, hs, None, None, rot, routing_score=score, **kw)
+        ref_orig = ev(attn, hs, None, None, rot, tau_sparse=0.3, routing_score=score, use_original_attn=True, **kw)
+        ctx = FX.det_tensor((1, 40, H * 128), 9).to(dev, torch.bfloat16)
+        ref_cross = ev(attn, hs, ctx, None, None, tau_sparse=0.3, routing_score=score, **kw)
+    SP_STATE.setup_sp_group(world)
+    s_loc = S // world
+    mine = hs[:, rank * s_loc:(rank + 1) * s_loc].contiguous()
+    with torch.no_grad():
+        got = all_gather(ev(attn, mine, None, None, rot, tau_sparse=0.3, routing_score=score, **kw), dim=1)
+        check("wan eval (top-1 routed)", got, ref_eval)
+        got = all_gather(tr(attn, mine, None, None, rot, routing_score=score, **kw), dim=1)
+        check("wan train (blend)", got, ref_train)
+        got = all_gather(ev(attn, mine, None, None, rot, tau_sparse=0.3, routing_score=score, use_original_attn=True,
+                            **kw), dim=1)
+        check("wan original attention", got, ref_orig)
+        got = all_gather(ev(attn, mine, ctx, None, None, tau_sparse=0.3, routing_score=score, **kw), dim=1)
+        check("wan cross attention", got, ref_cross)
+    SP_STATE._enabled, SP_STATE._sp_size = False, 1        # single-GPU reference for the next case
+
+    # ---------------- HunyuanVideo single-stream block with a padded text tail ----------------
+    lat, tile, win, lw, TL, TV = (2, 8, 8), (1, 4, 4), (3, 3, 3), (2, 2, 2), 16, 11
+    S = 128
+    hattn = FX.FakeHunyuanAttn(H, dual=False, seed=11).to(dev, torch.bfloat16)
+    hs = FX.det_tensor((1, S, H * 128), 12).to(dev, torch.bfloat16)
+    ehs = FX.det_tensor((1, TL, H * 128), 13).to(dev, torch.bfloat16)
+    mask = torch.zeros(1, 1, 1, S + TL, dtype=torch.bool, device=dev)
+    mask[..., :S + TV] = True
+    c, s = FX.hunyuan_rotary(S, 14)
+    rope = (c.to(dev), s.to(dev))
+    kw = dict(lowres_group_info=get_group_info(lat, lw, 0.5, device=dev), flex_attn_mask_func=None, window_size=win,
+              tile_size=tile, latent_shape=lat)
+    hev = HunyuanVideoFlashAttnProcessorTripleEval(check_input=True)
+    with torch.no_grad():
+        ref_v, ref_t = hev(hattn, hs, ehs, mask, rope, routing_score=score, tau_sparse=0.3, **kw)
+    SP_STATE._enabled, SP_STATE._sp_size = True, world
+    mine = hs[:, rank * (S // world):(rank + 1) * (S // world)].contiguous()
+    with torch.no_grad():
+        v, t = hev(hattn, mine, ehs, mask, rope, routing_score=score, tau_sparse=0.3, **kw)
+        check("hunyuan single-stream eval (video)", all_gather(v, dim=1), ref_v)
+        check("hunyuan single-stream eval (text)", t, ref_t)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

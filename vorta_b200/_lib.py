@@ -126,7 +126,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_ulysses_pack_heads.restype = C.c_int
     lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp]
     lib.vb_ulysses_pack_qkv.restype = C.c_int
-    lib.vb_ulysses_pack_qkv.argtypes = [vp, vp, vp, i64, i64, vp, i32, i32, i32, vp]
+    lib.vb_ulysses_pack_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i32, i32, i32, vp]
     lib.vb_ulysses_unpack_heads.restype = C.c_int
     lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, vp]
 

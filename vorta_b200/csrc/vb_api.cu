@@ -39,8 +39,9 @@ int launch_router(const void* temb, int temb_dtype, const void* w, const void* b
                   int heads, float tau, float* scores, int32_t* branch, cudaStream_t stream);
 int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
                            int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream);
-int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h,
-                            void* send, int s_loc, int heads, int world, cudaStream_t stream);
+int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                            const int64_t* stride_h, void* send, int s_loc, int heads, int world,
+                            cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
@@ -814,9 +815,9 @@ int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t head
   if (rc == VB_OK) ++g_launches;
   return rc;
 }
-int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h, void* send,
-                        int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream) {
-  VB_REQUIRE(q && k && v && send, VB_ERR_INVALID, "null argument");
+int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s, const int64_t* stride_h,
+                        void* send, int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream) {
+  VB_REQUIRE(q && k && v && send && stride_s && stride_h, VB_ERR_INVALID, "null argument");
   int rc = launch_ulysses_pack_qkv(q, k, v, stride_s, stride_h, send, s_loc, heads, world,
                                    static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;

@@ -348,10 +348,13 @@ vb_ulysses_permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst
 
 // q, k, v (S_loc, H, 128) with (token, head) strides -> send (3, P, S_loc, H/P, 128) in ONE pass; each tensor's
 // (P, S_loc, H/P, 128) block is the send buffer of one equal-split all-to-all.
+struct PackQkvParams {
+  const uint4* src[3];
+  int64_t stride_s[3], stride_h[3];   // elements
+};
+
 __global__ void __launch_bounds__(256)
-vb_ulysses_pack_qkv_kernel(const uint4* __restrict__ q, const uint4* __restrict__ k, const uint4* __restrict__ v,
-                           int64_t stride_s, int64_t stride_h, uint4* __restrict__ send, int s_loc, int heads,
-                           int world) {
+vb_ulysses_pack_qkv_kernel(const PackQkvParams p, uint4* __restrict__ send, int s_loc, int heads, int world) {
   const int hp = heads / world;
   const int64_t rows = static_cast<int64_t>(s_loc) * heads;
   const int64_t total = rows * 3 * 16;
@@ -363,22 +366,29 @@ vb_ulysses_pack_qkv_kernel(const uint4* __restrict__ q, const uint4* __restrict_
     r %= rows;
     const int h = static_cast<int>(r % heads);
     const int64_t s = r / heads;
-    const uint4* src = t == 0 ? q : (t == 1 ? k : v);
     const int64_t dst = ((((static_cast<int64_t>(t) * world + h / hp) * s_loc + s) * hp) + (h % hp)) * 16 + c;
-    send[dst] = src[(s * stride_s + h * stride_h) / 8 + c];
+    send[dst] = p.src[t][(s * p.stride_s[t] + h * p.stride_h[t]) / 8 + c];
   }
 }
 
-int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, int64_t stride_s, int64_t stride_h,
-                            void* send, int s_loc, int heads, int world, cudaStream_t stream) {
+int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                            const int64_t* stride_h, void* send, int s_loc, int heads, int world,
+                            cudaStream_t stream) {
   VB_REQUIRE(world > 0 && heads % world == 0, VB_ERR_INVALID, "heads %d not divisible by world %d", heads, world);
-  VB_REQUIRE(stride_s % 8 == 0 && stride_h % 8 == 0, VB_ERR_INVALID, "strides must be multiples of 8 elements");
+  PackQkvParams p;
+  p.src[0] = static_cast<const uint4*>(q);
+  p.src[1] = static_cast<const uint4*>(k);
+  p.src[2] = static_cast<const uint4*>(v);
+  for (int i = 0; i < 3; ++i) {
+    VB_REQUIRE(stride_s[i] % 8 == 0 && stride_h[i] % 8 == 0, VB_ERR_INVALID,
+               "strides must be multiples of 8 elements");
+    p.stride_s[i] = stride_s[i];
+    p.stride_h[i] = stride_h[i];
+  }
   const int64_t total = static_cast<int64_t>(s_loc) * heads * 3 * 16;
   if (total == 0) return VB_OK;
   const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  vb_ulysses_pack_qkv_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(q), static_cast<const uint4*>(k),
-                                                       static_cast<const uint4*>(v), stride_s, stride_h,
-                                                       static_cast<uint4*>(send), s_loc, heads, world);
+  vb_ulysses_pack_qkv_kernel<<<grid, 256, 0, stream>>>(p, static_cast<uint4*>(send), s_loc, heads, world);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }

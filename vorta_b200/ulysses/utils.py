@@ -52,7 +52,8 @@ def unpack_heads(recv: torch.Tensor) -> torch.Tensor:
 
 def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: int = 0
                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """q, k, v: (1, H, S_loc, 128) views sharing (token, head) strides: this rank's token shard, all heads.
+    """q, k, v: (1, H, S_loc, 128) views: this rank's token shard, all heads.
+    Each tensor may have its own (token, head) strides.
     Returns (1, H/P, S + extra_rows, 128) views of token-major memory: this rank's head chunk over the full
     sequence; ``extra_rows`` uninitialised rows are left at the end for the caller (HunyuanVideo text tokens)."""
     P = SP_STATE.sp_size
@@ -62,12 +63,15 @@ def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: 
     if H % P != 0:
         raise ValueError(f"heads {H} must be divisible by the sequence-parallel size {P}")
     for t in (q, k, v):
-        if t.stride(3) != 1 or t.stride(2) != q.stride(2) or t.stride(1) != q.stride(1):
-            raise ValueError("q, k, v must share (token, head) strides with contiguous channels")
+        if t.stride(3) != 1:
+            raise ValueError("q, k, v must have contiguous channels")
     hp = H // P
     send = torch.empty((3, P, s_loc, hp, D), dtype=q.dtype, device=q.device)
     with torch.cuda.device(q.device):
-        L.check(L.lib().vb_ulysses_pack_qkv(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(2), q.stride(1),
+        i64x3 = C.c_int64 * 3
+        L.check(L.lib().vb_ulysses_pack_qkv(q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                            i64x3(q.stride(2), k.stride(2), v.stride(2)),
+                                            i64x3(q.stride(1), k.stride(1), v.stride(1)),
                                             send.data_ptr(), s_loc, H, P, _stream(q.device)))
     out = []
     for i in range(3):
