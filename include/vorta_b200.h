@@ -187,6 +187,24 @@ void vb_stats_reset(void);
 int64_t vb_stats_launches(void);
 double vb_stats_attn_flops(void);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Fused elementwise kernels of the DiT block around the path ("next" rows).
+ * Rows are tokens, bf16, contiguous, `dim` channels (multiple of 8, <= 8192); fp32 math; one read + one write.
+ *   vb_block_ln_modulate : out = (LayerNorm(x) [* weight + bias]) [* (1 + scale) + shift]
+ *        replaces norm1/norm3 + adaLN modulate and norm2 (vorta/patch/modeling_wan.py:205-206, 226, 232-234);
+ *        weight/bias fp32 (dim) or NULL; scale/shift fp32 (batch, dim) or NULL; batch = row / rows_per_batch
+ *   vb_block_gate_residual: out = x + y * gate  (gate fp32 (batch, dim), NULL = plain add)   (:225, :229, :238)
+ *   vb_block_rmsnorm_rope : RMSNorm over the whole row * weight (bf16, dim), then the complex rotation of channel
+ *        pairs of every 128-wide head by (cos, sin) fp32 (tokens_per_batch, 64); token = row % tokens_per_batch.
+ *        NULL tables = norm only.  replaces norm_q/norm_k + apply_rotary_emb (vorta/attention/wan.py:85-100, 34-37)
+ * ---------------------------------------------------------------------------------------------------- */
+int vb_block_ln_modulate(const void* x, const float* weight, const float* bias, const float* scale, const float* shift,
+                         void* out, int64_t rows, int32_t dim, int32_t rows_per_batch, float eps, vb_stream_t stream);
+int vb_block_gate_residual(const void* x, const void* y, const float* gate, void* out, int64_t rows, int32_t dim,
+                           int32_t rows_per_batch, vb_stream_t stream);
+int vb_block_rmsnorm_rope(const void* x, const void* weight, const float* cos_tab, const float* sin_tab, void* out,
+                          int64_t rows, int32_t dim, int32_t tokens_per_batch, float eps, vb_stream_t stream);
+
 /* Live timing of the attention kernel for the roofline line of bench.py: while enabled, every launch of the
  * tcgen05 attention kernel is bracketed by CUDA events on its own stream; vb_timing_collect waits for them and
  * returns the summed kernel time (ms), the number of launches and their algorithmic FLOPs, then clears. */

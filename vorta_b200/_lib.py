@@ -11,7 +11,7 @@ import subprocess
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvorta_b200.so")
+LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(_HERE, "lib", "libvorta_b200.so")   # override: perf experiments
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 VB_OK = 0
@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "vb_plan_create", "vb_plan_destroy", "vb_plan_set_text_valid", "vb_plan_query", "vb_plan_export",
     "vb_router_forward", "vb_coreset_select", "vb_coreset_tables", "vb_gather_rows",
     "vb_attn_workspace_bytes", "vb_attn_fwd", "vb_attn_dense",
+    "vb_block_ln_modulate", "vb_block_gate_residual", "vb_block_rmsnorm_rope",
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
     "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_unpack_heads",
 )
@@ -119,6 +120,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_stats_reset.restype = None
     lib.vb_stats_launches.restype = i64
     lib.vb_stats_attn_flops.restype = C.c_double
+    lib.vb_block_ln_modulate.restype = C.c_int
+    lib.vb_block_ln_modulate.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, vp]
+    lib.vb_block_gate_residual.restype = C.c_int
+    lib.vb_block_gate_residual.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.vb_block_rmsnorm_rope.restype = C.c_int
+    lib.vb_block_rmsnorm_rope.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, f32, vp]
     lib.vb_timing_enable.restype = None
     lib.vb_timing_enable.argtypes = [C.c_int]
     lib.vb_timing_collect.restype = C.c_int

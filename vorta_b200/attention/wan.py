@@ -33,6 +33,36 @@ def apply_rotary_emb(hidden_states: torch.Tensor, freqs: torch.Tensor) -> torch.
     return out.type_as(hidden_states)
 
 
+_ROPE_CACHE = {}
+
+
+def _rope_tables(rotary_emb: torch.Tensor):
+    """fp32 (S_loc, 64) cos / sin tables of a complex (1, 1, S_loc, 64) phase tensor; the same tensor object is
+    handed to every block of a forward, so the last conversion is cached."""
+    key = (rotary_emb.data_ptr(), tuple(rotary_emb.shape), rotary_emb.storage_offset())
+    hit = _ROPE_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    r = rotary_emb.reshape(rotary_emb.shape[-2], rotary_emb.shape[-1])
+    cos, sin = r.real.float().contiguous(), r.imag.float().contiguous()
+    _ROPE_CACHE["last"] = (key, cos, sin, rotary_emb)       # keep the source alive so the pointer stays unique
+    return cos, sin
+
+
+def _norm_rope(norm, x: torch.Tensor, cos, sin) -> torch.Tensor:
+    """norm_q / norm_k (RMSNorm across heads) followed by RoPE, fused; plain RoPE when the module has no norm."""
+    if norm is not None and getattr(norm, "weight", None) is not None and x.is_contiguous():
+        eps = norm.eps if getattr(norm, "eps", None) is not None else torch.finfo(x.dtype).eps
+        return ops.rmsnorm_rope(x, norm.weight, eps, cos, sin)
+    if norm is not None:
+        x = norm(x)
+    if cos is not None:
+        heads = x.shape[-1] // 128
+        x = apply_rotary_emb(x.unflatten(2, (heads, -1)).transpose(1, 2),
+                             torch.complex(cos, sin)[None, None]).transpose(1, 2).flatten(2, 3)
+    return x
+
+
 def _top1_branches(routing_score: torch.Tensor, tau_sparse: Optional[float]) -> Sequence[int]:
     """wan.py:396-400: the first sample's top-1 expert per head; below ``tau_sparse`` -> full attention."""
     score, idx = routing_score[0].float().topk(1, dim=-1)
@@ -66,18 +96,16 @@ class WanAttnProcessor2_0:
         query = attn.to_q(hidden_states)
         key = attn.to_k(encoder_hidden_states)
         value = attn.to_v(encoder_hidden_states)
-        if attn.norm_q is not None:
-            query = attn.norm_q(query)
-        if attn.norm_k is not None:
-            key = attn.norm_k(key)
+        cos = sin = None
+        if rotary_emb is not None:
+            cos, sin = _rope_tables(shrink_dim(rotary_emb, dim=2))
+        # RMSNorm across heads + RoPE in one pass per tensor (reference: bf16 RMSNorm, then complex128 RoPE)
+        query = _norm_rope(attn.norm_q, query, cos, sin)
+        key = _norm_rope(attn.norm_k, key, cos, sin)
         # (B, S, H*D) -> (B, H, S, D) as a VIEW: the kernels take the strides
         query = query.unflatten(2, (attn.heads, -1)).transpose(1, 2)
         key = key.unflatten(2, (attn.heads, -1)).transpose(1, 2)
         value = value.unflatten(2, (attn.heads, -1)).transpose(1, 2)
-        if rotary_emb is not None:
-            rotary_emb = shrink_dim(rotary_emb, dim=2)
-            query = apply_rotary_emb(query, rotary_emb)
-            key = apply_rotary_emb(key, rotary_emb)
         return query, key, value, encoder_hidden_states_img
 
     def _attn(self, attn, query, key, value, attention_mask, encoder_hidden_states_img, is_cross_attn: bool,

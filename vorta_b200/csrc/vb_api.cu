@@ -42,6 +42,12 @@ int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int
 int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                             const int64_t* stride_h, void* send, int s_loc, int heads, int world,
                             cudaStream_t stream);
+int launch_ln_modulate(const void* x, const float* w, const float* b, const float* scale, const float* shift, void* out,
+                       int64_t rows, int dim, int rows_per_batch, float eps, cudaStream_t stream);
+int launch_gate_residual(const void* x, const void* y, const float* gate, void* out, int64_t rows, int dim,
+                         int rows_per_batch, cudaStream_t stream);
+int launch_rmsnorm_rope(const void* x, const void* weight, const float* cs, const float* sn, void* out, int64_t rows,
+                        int dim, int tokens_per_batch, float eps, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
@@ -778,6 +784,32 @@ int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const 
   std::vector<AttnHead> hs(heads);
   for (int h = 0; h < heads; ++h) hs[h] = AttnHead{h, h, 1.f, 0};
   return run_branch(bl, a, hs, 0, batch, static_cast<cudaStream_t>(stream_));
+}
+
+int vb_block_ln_modulate(const void* x, const float* weight, const float* bias, const float* scale, const float* shift,
+                         void* out, int64_t rows, int32_t dim, int32_t rows_per_batch, float eps, vb_stream_t stream) {
+  VB_REQUIRE(x && out, VB_ERR_INVALID, "null argument");
+  VB_REQUIRE((scale == nullptr) == (shift == nullptr), VB_ERR_INVALID, "scale and shift come together");
+  int rc = launch_ln_modulate(x, weight, bias, scale, shift, out, rows, dim, rows_per_batch, eps,
+                              static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_block_gate_residual(const void* x, const void* y, const float* gate, void* out, int64_t rows, int32_t dim,
+                           int32_t rows_per_batch, vb_stream_t stream) {
+  VB_REQUIRE(x && y && out, VB_ERR_INVALID, "null argument");
+  int rc = launch_gate_residual(x, y, gate, out, rows, dim, rows_per_batch, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_block_rmsnorm_rope(const void* x, const void* weight, const float* cos_tab, const float* sin_tab, void* out,
+                          int64_t rows, int32_t dim, int32_t tokens_per_batch, float eps, vb_stream_t stream) {
+  VB_REQUIRE(x && weight && out, VB_ERR_INVALID, "null argument");
+  VB_REQUIRE((cos_tab == nullptr) == (sin_tab == nullptr), VB_ERR_INVALID, "cos and sin tables come together");
+  int rc = launch_rmsnorm_rope(x, weight, cos_tab, sin_tab, out, rows, dim, tokens_per_batch, eps,
+                               static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
 }
 
 void vb_timing_enable(int on) { g_timing = on != 0; }

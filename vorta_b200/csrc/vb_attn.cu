@@ -50,6 +50,22 @@ struct BlockWalker {
   }
 };
 
+#ifdef VB_TIMELINE               // perf experiment: clock stamps of CTA (0,0,0) -> p.dbg as int64[who][block][8]
+#define VB_STAMP(who, j, slot)                                                                         \
+  do {                                                                                                 \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64)         \
+      reinterpret_cast<long long*>(p.dbg)[((who) * 64 + (j)) * 8 + (slot)] = clock64();                \
+  } while (0)
+#else
+#define VB_STAMP(who, j, slot) do {} while (0)
+#endif
+
+#ifdef VB_EXP_NOMUFU            // perf experiment: softmax without the MUFU ex2 (results are garbage)
+#define VB_EXP2(x) ((x) * 0.001f)
+#else
+#define VB_EXP2(x) fast_exp2(x)
+#endif
+
 __device__ __forceinline__ int count_blocks(const KvRun* runs, int n_runs) {
   int n = 0;
   for (int r = 0; r < n_runs; ++r) n += (runs[r].len + kBlockN - 1) / kBlockN;
@@ -140,65 +156,85 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else if (warp == 9) {
     // ======================================= MMA issuer =========================================
-    if (lane == 0 && n_blocks > 0) {
+    // The whole warp runs this role converged and every address below is made warp-uniform, so descriptors live
+    // in uniform registers and one elected lane issues; a single-lane role pays a register->uniform "waterfall"
+    // per operand (measured: ~250 SASS instructions per 16 MMAs, the round-1 bottleneck).
+    const int nblk = __shfl_sync(0xffffffffu, n_blocks, 0);
+    const int nq_u = __shfl_sync(0xffffffffu, nq, 0);
+    if (nblk > 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
-      const uint32_t v_lbo = p.dbg_v_lbo ? p.dbg_v_lbo : (uint32_t)kHalfBytes;
-      const uint32_t v_sbo = p.dbg_v_sbo ? p.dbg_v_sbo : 1024u;
+      // descriptor = hi:lo; hi = SBO (1024 B) | version 1 | SWIZZLE_128B, identical for Q, K and V
+      constexpr uint64_t desc_hi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+      constexpr uint32_t lbo_k = 1u << 16;                          // K-major: LBO field = 1 (16 B, unused)
+      constexpr uint32_t lbo_v = (kHalfBytes >> 4) << 16;           // MN-major V: LBO = 16 KB between channel halves
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t q_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_q) & 0x3FFFFu) >> 4, 0);
+      const uint32_t kv_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_kv) & 0x3FFFFu) >> 4, 0);
 
       auto issue_qk = [&](int t, uint32_t slot) {
-        const uint32_t qa = smem_u32(smem_q + t * kTileBytes);
-        const uint32_t kb = smem_u32(smem_kv + slot * kTileBytes);
-        const uint32_t d = tmem_base + t * kBlockN;
+        const uint32_t a0 = q_lo + t * (kTileBytes >> 4) + lbo_k;
+        const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_k;
+        const uint32_t d = tb + t * kBlockN;
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k) {
-          // K-major, 64-element (128 B) swizzled rows: 16 elements = 32 B inside the atom, 64 elements = next half
-          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-          umma_ss(d, umma_smem_desc(qa + off, 16, 1024), umma_smem_desc(kb + off, 16, 1024), idesc_qk, k > 0);
+          // K-major 128 B swizzled rows: 16 channels = 32 B inside the atom, 64 channels = the other half
+          const uint32_t off = (k >> 2) * (kHalfBytes >> 4) + (k & 3) * 2;
+          umma_ss(d, desc_hi | (a0 + off), desc_hi | (b0 + off), idesc_qk, k > 0);
         }
       };
       auto issue_pv = [&](int t, uint32_t slot, uint32_t accumulate) {
-        const uint32_t vb_ = smem_u32(smem_kv + slot * kTileBytes);
-        const uint32_t d = tmem_base + 2 * kBlockN + t * kHeadDim;
-        const uint32_t a = tmem_base + t * kBlockN;     // P_t: packed bf16 pairs, 8 columns per 16 keys
+        const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_v;
+        const uint32_t d = tb + 2 * kBlockN + t * kHeadDim;
+        const uint32_t a = tb + t * kBlockN;            // P_t: packed bf16 pairs, 8 columns per 16 keys
 #pragma unroll
         for (int k = 0; k < kBlockN / 16; ++k) {
-          // V block is [128 keys][128 d]: MN(d)-major, 16 keys = 16 rows x 128 B = 2048 B
-          umma_ts(d, a + k * 8, umma_smem_desc(vb_ + k * 2048, v_lbo, v_sbo), idesc_pv, accumulate | (k > 0));
+          // V block [128 keys][128 channels], MN-major: 16 keys = 16 rows x 128 B = 2048 B
+          umma_ts(d, a + k * 8, desc_hi | (b0 + k * (2048 >> 4)), idesc_pv, accumulate | (k > 0));
         }
       };
 
-      for (int t = 0; t < nq; ++t) mbar_wait(&bar_q_full[t], 0);
+      for (int t = 0; t < nq_u; ++t) mbar_wait(&bar_q_full[t], 0);
       mbar_wait(&bar_slot_full[0], 0);   // K(0) is load 0
       tc_fence_after();
-      for (int t = 0; t < nq; ++t) {
-        issue_qk(t, 0);
-        umma_commit(&bar_s_full[t]);
+      if (elect_one()) {
+        for (int t = 0; t < nq_u; ++t) {
+          issue_qk(t, 0);
+          umma_commit(&bar_s_full[t]);
+        }
+        umma_commit(&bar_slot_empty[0]);
       }
-      umma_commit(&bar_slot_empty[0]);
+      __syncwarp();
 
-      for (int j = 0; j < n_blocks; ++j) {
+      for (int j = 0; j < nblk; ++j) {
         const uint32_t v_idx = 2 * j + 1, v_slot = v_idx % kNumSlots, v_phase = (v_idx / kNumSlots) & 1u;
         const uint32_t k_idx = 2 * j + 2, k_slot = k_idx % kNumSlots, k_phase = (k_idx / kNumSlots) & 1u;
-        const bool more = j + 1 < n_blocks;
+        const bool more = j + 1 < nblk;
+        // operand waits first: TMA runs far ahead, so these are off the critical path; the softmax -> P hand-off
+        // below is ON it (round-1 timeline: every extra wait after p_ready costs ~100-300 cycles of tensor idle)
         mbar_wait(&bar_slot_full[v_slot], v_phase);
-        for (int t = 0; t < nq; ++t) {
+        if (more) mbar_wait(&bar_slot_full[k_slot], k_phase);
+        for (int t = 0; t < nq_u; ++t) {
           mbar_wait(&bar_p_ready[t], j & 1);
+          if (lane == 0) VB_STAMP(2 + t, j, 0);
           tc_fence_after();
-          issue_pv(t, v_slot, j > 0);
-          if (more) {
-            if (t == 0) {
-              mbar_wait(&bar_slot_full[k_slot], k_phase);
-              tc_fence_after();
+          if (lane == 0) VB_STAMP(2 + t, j, 1);
+          if (elect_one()) {
+            issue_pv(t, v_slot, j > 0);
+            if (more) {
+              issue_qk(t, k_slot);
+              umma_commit(&bar_s_full[t]);
+            } else {
+              umma_commit(&bar_o_full[t]);
             }
-            issue_qk(t, k_slot);
-            umma_commit(&bar_s_full[t]);
-          } else {
-            umma_commit(&bar_o_full[t]);
+            if (t == nq_u - 1) {
+              umma_commit(&bar_slot_empty[v_slot]);
+              if (more) umma_commit(&bar_slot_empty[k_slot]);
+            }
           }
+          __syncwarp();
+          if (lane == 0) VB_STAMP(2 + t, j, 2);
         }
-        umma_commit(&bar_slot_empty[v_slot]);
-        if (more) umma_commit(&bar_slot_empty[k_slot]);
       }
     }
   } else {
@@ -215,13 +251,21 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       BlockWalker w(s_runs, n_runs);
       int row0, valid;
       for (int j = 0; w.next(row0, valid); ++j) {
+        if (row == 0) VB_STAMP(t, j, 0);
         mbar_wait(&bar_s_full[t], j & 1);
         tc_fence_after();
+        if (row == 0) VB_STAMP(t, j, 1);
+#ifdef VB_EXP_SKIP_SOFTMAX   // perf experiment: tensor-pipe-only throughput (results are garbage)
+        tc_fence_before();
+        mbar_arrive(&bar_p_ready[t]);
+        continue;
+#endif
         uint32_t s[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, s[c]);
         tmem_ld_wait();
-
+        if (row == 0) VB_STAMP(t, j, 2);
+#ifndef VB_TIMELINE
         if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
           float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN;   // raw scores of block 0
 #pragma unroll
@@ -229,6 +273,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(s[c][i]);
         }
+#endif
 
         if (valid < kBlockN) {   // run tail: keys beyond the run do not exist for this query
 #pragma unroll
@@ -272,10 +317,10 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const int c = hp * 2 + cc;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float e0 = fast_exp2(fmaf(__uint_as_float(s[c][i + 0]), scale, -m_ref));
-              const float e1 = fast_exp2(fmaf(__uint_as_float(s[c][i + 1]), scale, -m_ref));
-              const float e2 = fast_exp2(fmaf(__uint_as_float(s[c][i + 2]), scale, -m_ref));
-              const float e3 = fast_exp2(fmaf(__uint_as_float(s[c][i + 3]), scale, -m_ref));
+              const float e0 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 0]), scale, -m_ref));
+              const float e1 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 1]), scale, -m_ref));
+              const float e2 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 2]), scale, -m_ref));
+              const float e3 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 3]), scale, -m_ref));
               sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
               pk[cc * 16 + (i >> 1) + 0] = pack_bf16x2(e0, e1);
               pk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
@@ -284,6 +329,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           tmem_st32(s_addr + hp * 32, pk);   // P_t(j): keys [64 hp, 64 hp + 64) -> 32 columns of bf16 pairs
         }
         l_sum += (sum0 + sum1) + (sum2 + sum3);
+        if (row == 0) VB_STAMP(t, j, 3);
 
         if (rescale) {
           // PV_t(j-1) completed before S_t(j) was signalled (commit order), PV_t(j) waits for our arrive:
@@ -299,8 +345,10 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
         }
         tmem_st_wait();
+        if (row == 0) VB_STAMP(t, j, 4);
         tc_fence_before();
         mbar_arrive(&bar_p_ready[t]);
+        if (row == 0) VB_STAMP(t, j, 5);
       }
 
       // ------------------------------------ epilogue ------------------------------------
@@ -328,12 +376,14 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         uint32_t o[32];
         tmem_ld32(o_addr + c * 32, o);
         tmem_ld_wait();
+#ifndef VB_TIMELINE
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
           float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim;
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(o[i]);   // un-normalised O
           if (c == 0) p.dbg[4 * kBlockM * kBlockN + t * kBlockM + row] = l_sum;
         }
+#endif
         for (int dsti = 0; dsti < n_dst; ++dsti) {
           const int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
           uint4* dst = reinterpret_cast<uint4*>(out_head + tok * p.out_stride_s + c * 32);

@@ -1,0 +1,202 @@
+// vb_block.cu — fused elementwise kernels of the DiT block AROUND the attention path:
+//   LayerNorm (+ affine) (+ adaLN modulate)          modeling_wan.py:205-206, 226, 232-234
+//   gated residual  out = x + y * gate                modeling_wan.py:225, 238
+//   RMSNorm-across-heads + RoPE on Q / K              wan.py:85-100 (reference: RMSNorm in bf16, RoPE in complex128)
+// All HBM-bound: one CTA per token row, 16-byte vectors, fp32 math, a single read and a single write per element.
+#include "vb_common.cuh"
+
+namespace vb {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxVec = 4;   // 16-byte vectors per thread -> rows up to 256 * 4 * 8 = 8192 channels
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i + 0] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+// block-wide sum of two values (blockDim.x == kRowThreads)
+__device__ __forceinline__ void block_sum2(float& a, float& b) {
+  __shared__ float red[2][kRowThreads / 32];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = a; red[1][w] = b; }
+  __syncthreads();
+  a = l < kRowThreads / 32 ? red[0][l] : 0.f;
+  b = l < kRowThreads / 32 ? red[1][l] : 0.f;
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  a = __shfl_sync(0xffffffffu, a, 0);
+  b = __shfl_sync(0xffffffffu, b, 0);
+  __syncthreads();
+}
+
+// out = (LN(x) [* w + b]) [* (1 + scale) + shift]; scale / shift are fp32 per (batch, channel)
+__global__ void __launch_bounds__(kRowThreads)
+vb_ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                      const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                      int dim, int rows_per_batch, float eps) {
+  const int64_t row = blockIdx.x;
+  const int nvec = dim >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * dim);
+  float v[kMaxVec][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = threadIdx.x + i * kRowThreads;
+    if (idx < nvec) {
+      unpack8(xr[idx], v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1 += v[i][e]; s2 += v[i][e] * v[i][e]; }
+    }
+  }
+  block_sum2(s1, s2);
+  const float mean = s1 / dim;
+  const float rstd = rsqrtf(fmaxf(s2 / dim - mean * mean, 0.f) + eps);
+  const int64_t batch = row / rows_per_batch;
+  const float* sc = scale ? scale + batch * dim : nullptr;
+  const float* sh = shift ? shift + batch * dim : nullptr;
+  uint4* orow = reinterpret_cast<uint4*>(out + row * dim);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = threadIdx.x + i * kRowThreads;
+    if (idx < nvec) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = idx * 8 + e;
+        float t = (v[i][e] - mean) * rstd;
+        if (w) t = t * w[c] + (b ? b[c] : 0.f);
+        if (sc) t = t * (1.f + sc[c]) + sh[c];
+        y[e] = t;
+      }
+      orow[idx] = pack8(y);
+    }
+  }
+}
+
+// out = x + y * gate (gate fp32 per (batch, channel); nullptr = plain residual add)
+__global__ void __launch_bounds__(256)
+vb_gate_residual_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const float* __restrict__ gate,
+                        uint4* __restrict__ out, int64_t n_vec, int dim, int64_t vec_per_batch) {
+  const int dvec = dim >> 3;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[8], c[8];
+    unpack8(x[i], a);
+    unpack8(y[i], c);
+    if (gate) {
+      const float* g = gate + (i / vec_per_batch) * dim + (i % dvec) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = fmaf(c[e], g[e], a[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += c[e];
+    }
+    out[i] = pack8(a);
+  }
+}
+
+// RMSNorm over the whole row (all heads) * weight, then RoPE on channel pairs of every 128-wide head.
+// cos / sin: fp32 (tokens, 64) for the rank's token shard; token = row % tokens_per_batch
+__global__ void __launch_bounds__(kRowThreads)
+vb_rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ weight,
+                       const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
+                       int dim, int tokens_per_batch, float eps) {
+  const int64_t row = blockIdx.x;
+  const int nvec = dim >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * dim);
+  const uint4* wr = reinterpret_cast<const uint4*>(weight);
+  float v[kMaxVec][8];
+  float s2 = 0.f, dummy = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = threadIdx.x + i * kRowThreads;
+    if (idx < nvec) {
+      unpack8(xr[idx], v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s2 += v[i][e] * v[i][e];
+    }
+  }
+  block_sum2(s2, dummy);
+  const float rinv = rsqrtf(s2 / dim + eps);
+  const int64_t tok = row % tokens_per_batch;
+  const float* c_row = cs ? cs + tok * (kHeadDim / 2) : nullptr;
+  const float* s_row = sn ? sn + tok * (kHeadDim / 2) : nullptr;
+  uint4* orow = reinterpret_cast<uint4*>(out + row * dim);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = threadIdx.x + i * kRowThreads;
+    if (idx < nvec) {
+      float wv[8], y[8];
+      unpack8(wr[idx], wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = v[i][e] * rinv * wv[e];
+      if (c_row) {
+        const int pair0 = ((idx * 8) & (kHeadDim - 1)) >> 1;     // first channel pair of this vector inside its head
+#pragma unroll
+        for (int pz = 0; pz < 4; ++pz) {
+          const float c = c_row[pair0 + pz], s = s_row[pair0 + pz];
+          const float re = y[2 * pz], im = y[2 * pz + 1];
+          y[2 * pz] = re * c - im * s;
+          y[2 * pz + 1] = re * s + im * c;
+        }
+      }
+      orow[idx] = pack8(y);
+    }
+  }
+}
+
+int launch_ln_modulate(const void* x, const float* w, const float* b, const float* scale, const float* shift, void* out,
+                       int64_t rows, int dim, int rows_per_batch, float eps, cudaStream_t stream) {
+  VB_REQUIRE(dim % 8 == 0 && dim <= kRowThreads * kMaxVec * 8, VB_ERR_UNSUPPORTED, "row width %d not supported", dim);
+  if (rows == 0) return VB_OK;
+  vb_ln_modulate_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), w, b, scale, shift, static_cast<__nv_bfloat16*>(out), dim, rows_per_batch, eps);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+int launch_gate_residual(const void* x, const void* y, const float* gate, void* out, int64_t rows, int dim,
+                         int rows_per_batch, cudaStream_t stream) {
+  VB_REQUIRE(dim % 8 == 0, VB_ERR_UNSUPPORTED, "row width %d not supported", dim);
+  const int64_t n_vec = rows * (dim >> 3);
+  if (n_vec == 0) return VB_OK;
+  const int64_t blocks = (n_vec + 255) / 256;
+  const int grid = static_cast<int>(blocks < 148 * 32 ? blocks : 148 * 32);
+  vb_gate_residual_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(y), gate,
+                                                    static_cast<uint4*>(out), n_vec, dim,
+                                                    static_cast<int64_t>(rows_per_batch) * (dim >> 3));
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+int launch_rmsnorm_rope(const void* x, const void* weight, const float* cs, const float* sn, void* out, int64_t rows,
+                        int dim, int tokens_per_batch, float eps, cudaStream_t stream) {
+  VB_REQUIRE(dim % kHeadDim == 0 && dim <= kRowThreads * kMaxVec * 8, VB_ERR_UNSUPPORTED,
+             "row width %d not supported", dim);
+  if (rows == 0) return VB_OK;
+  vb_rmsnorm_rope_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight), cs, sn,
+      static_cast<__nv_bfloat16*>(out), dim, tokens_per_batch, eps);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb

@@ -88,6 +88,10 @@ class FeedForward(nn.Module):
         self.proj_out = nn.Linear(ffn_dim, dim)
 
     def forward(self, x):
+        if x.is_cuda and x.dim() == 3:
+            # bias + tanh-GELU in the cuBLASLt epilogue of the first GEMM: no separate pass over (S, ffn_dim)
+            h = torch._addmm_activation(self.proj_in.bias, x.flatten(0, 1), self.proj_in.weight.t(), use_gelu=True)
+            return self.proj_out(h).unflatten(0, x.shape[:2])
         return self.proj_out(self.act(self.proj_in(x)))
 
 

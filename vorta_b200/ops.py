@@ -295,3 +295,73 @@ def timing_collect() -> Tuple[float, int, float]:
     ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
     L.check(L.lib().vb_timing_collect(C.byref(ms), C.byref(n), C.byref(fl)))
     return float(ms.value), int(n.value), float(fl.value)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused elementwise kernels of the DiT block around the path
+# ---------------------------------------------------------------------------------------------------------
+def _rows(x: torch.Tensor):
+    if not x.is_cuda:
+        raise L.VortaB200Error("block kernels need CUDA tensors: vorta_b200 has no CPU path")
+    if x.dtype != torch.bfloat16 or x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("block kernels need contiguous bf16 tensors of shape (B, S, dim)")
+    return x.shape[0] * x.shape[1], x.shape[2], x.shape[1]
+
+
+def _contig(x: torch.Tensor) -> torch.Tensor:
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def _f32(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+def ln_modulate(x: torch.Tensor, weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                eps: float = 1e-6) -> torch.Tensor:
+    """(LayerNorm(x) [* weight + bias]) [* (1 + scale) + shift] in fp32, one pass (modeling_wan.py:205-206)."""
+    x = _contig(x)
+    rows, dim, per_batch = _rows(x)
+    weight, bias, scale, shift = _f32(weight), _f32(bias), _f32(scale), _f32(shift)
+    out = torch.empty_like(x)
+    p = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(x.device):
+        L.check(L.lib().vb_block_ln_modulate(x.data_ptr(), p(weight), p(bias), p(scale), p(shift), out.data_ptr(), rows,
+                                             dim, per_batch, float(eps), _stream_ptr(x.device)))
+    return out
+
+
+def gate_residual(x: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x + y * gate in fp32, one pass (modeling_wan.py:225, 238); gate (B, dim) fp32 or None."""
+    x = _contig(x)
+    rows, dim, per_batch = _rows(x)
+    if y.shape != x.shape:
+        raise ValueError("gate_residual: shape mismatch")
+    if not y.is_contiguous():
+        y = y.contiguous()
+    gate = _f32(gate)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().vb_block_gate_residual(x.data_ptr(), y.data_ptr(), gate.data_ptr() if gate is not None else None,
+                                               out.data_ptr(), rows, dim, per_batch, _stream_ptr(x.device)))
+    return out
+
+
+def rmsnorm_rope(x: torch.Tensor, weight: torch.Tensor, eps: float, cos: Optional[torch.Tensor] = None,
+                 sin: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RMSNorm across heads * weight, then RoPE per 128-wide head (wan.py:85-100); cos / sin fp32 (S, 64)."""
+    x = _contig(x)
+    rows, dim, per_batch = _rows(x)
+    w = weight if weight.dtype == torch.bfloat16 and weight.is_contiguous() else weight.to(torch.bfloat16).contiguous()
+    out = torch.empty_like(x)
+    if cos is not None and (tuple(cos.shape) != (per_batch, HEAD_DIM // 2) or cos.dtype != torch.float32):
+        raise ValueError(f"cos / sin tables must be fp32 ({per_batch}, {HEAD_DIM // 2}), got {tuple(cos.shape)}")
+    with torch.cuda.device(x.device):
+        L.check(L.lib().vb_block_rmsnorm_rope(x.data_ptr(), w.data_ptr(), cos.data_ptr() if cos is not None else None,
+                                              sin.data_ptr() if sin is not None else None, out.data_ptr(), rows, dim,
+                                              per_batch, float(eps), _stream_ptr(x.device)))
+    return out

@@ -16,6 +16,7 @@ from typing import Any, Dict, Optional
 
 import torch
 
+from .. import ops
 from ..attention import WanAttnProcessor2_0, WanAttnProcessorTripleEval, WanAttnProcessorTripleTrain
 from ..ulysses import SP_STATE, all_gather
 from .router import Router, route_step
@@ -41,10 +42,12 @@ def wan_block_routed_forward(self, hidden_states, encoder_hidden_states, temb, r
                              routing_score: Optional[torch.Tensor] = None, branch=None):
     """Dataflow of modeling_wan.py:195-239.  ``routing_score`` / ``branch`` may be supplied by the caller when the
     step's routing was precomputed; otherwise the block's router runs here like in the reference."""
+    # adaLN parameters in fp32, (B, dim) each; every elementwise stage below is ONE fused pass with fp32 math
+    # (the reference runs them as chains of fp32 torch ops, modeling_wan.py:201-238)
     shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = (
-        self.scale_shift_table + temb.float()).chunk(6, dim=1)
+        t.contiguous() for t in (self.scale_shift_table + temb.float()).unbind(dim=1))
 
-    norm_hidden_states = (self.norm1(hidden_states.float()) * (1 + scale_msa) + shift_msa).type_as(hidden_states)
+    norm_hidden_states = ops.ln_modulate(hidden_states, None, None, scale_msa, shift_msa, self.norm1.eps)
     if not use_original_attn and routing_score is None:
         routing_score = self.router(temb_before_proj)
     kwargs = dict(self_attention_kwargs or {})
@@ -52,15 +55,15 @@ def wan_block_routed_forward(self, hidden_states, encoder_hidden_states, temb, r
         kwargs["branch"] = branch
     attn_output = self.attn1(hidden_states=norm_hidden_states, rotary_emb=rotary_emb, routing_score=routing_score,
                              use_original_attn=use_original_attn, **kwargs)
-    hidden_states = (hidden_states.float() + attn_output * gate_msa).type_as(hidden_states)
+    hidden_states = ops.gate_residual(hidden_states, attn_output, gate_msa)
 
-    norm_hidden_states = self.norm2(hidden_states.float()).type_as(hidden_states)
+    norm_hidden_states = ops.ln_modulate(hidden_states, self.norm2.weight, self.norm2.bias, None, None, self.norm2.eps)
     attn_output = self.attn2(hidden_states=norm_hidden_states, encoder_hidden_states=encoder_hidden_states)
-    hidden_states = hidden_states + attn_output
+    hidden_states = ops.gate_residual(hidden_states, attn_output, None)
 
-    norm_hidden_states = (self.norm3(hidden_states.float()) * (1 + c_scale_msa) + c_shift_msa).type_as(hidden_states)
+    norm_hidden_states = ops.ln_modulate(hidden_states, None, None, c_scale_msa, c_shift_msa, self.norm3.eps)
     ff_output = self.ffn(norm_hidden_states)
-    hidden_states = (hidden_states.float() + ff_output.float() * c_gate_msa).type_as(hidden_states)
+    hidden_states = ops.gate_residual(hidden_states, ff_output, c_gate_msa)
     return hidden_states, routing_score
 
 
@@ -99,8 +102,9 @@ def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timeste
         if return_routing_scores:
             routing_scores.append(score_i)
 
-    shift, scale = (self.scale_shift_table + temb.unsqueeze(1)).chunk(2, dim=1)
-    hidden_states = (self.norm_out(hidden_states.float()) * (1 + scale) + shift).type_as(hidden_states)
+    shift, scale = ((self.scale_shift_table.float() + temb.float().unsqueeze(1))).unbind(dim=1)
+    hidden_states = ops.ln_modulate(hidden_states, None, None, scale.contiguous(), shift.contiguous(),
+                                    self.norm_out.eps)
     hidden_states = self.proj_out(hidden_states)
     if SP_STATE.enabled:
         hidden_states = all_gather(hidden_states, dim=1)
