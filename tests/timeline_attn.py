@@ -28,6 +28,10 @@ for who in (0, 1):
     print(f"tile{who}: wait {float((d[:,1]-d[:,0]).float().mean()):.0f} ld {float((d[:,2]-d[:,1]).float().mean()):.0f} "
           f"compute {float((d[:,3]-d[:,2]).float().mean()):.0f} st_wait {float((d[:,4]-d[:,3]).float().mean()):.0f} "
           f"s_ready->arrived {float((d[:,5]-d[:,1]).float().mean()):.0f}")
+for who in (0, 1):
+    d = t[who, 8:40]
+    print(f"tile{who}: ld_done->max+pair_sync {float((d[:,6]-d[:,2]).float().mean()):.0f}  ->first32 exps {float((d[:,7]-d[:,6]).float().mean()):.0f}"
+          f"  ->all exps {float((d[:,3]-d[:,7]).float().mean()):.0f}")
 m = t[2:4, 8:40]
 print("mma: p_seen->issued", float((m[:, :, 2] - m[:, :, 0]).float().mean()))
 # latency from softmax arrive to MMA seeing it, and from MMA issue end to S ready of next block

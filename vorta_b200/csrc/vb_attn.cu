@@ -25,9 +25,32 @@ namespace vb {
 constexpr int kNumSlots = 5;                       // K/V ring
 constexpr int kTileBytes = kBlockN * kHeadDim * 2; // 32 KB: one 128x128 bf16 block = two 128x64 swizzled halves
 constexpr int kHalfBytes = kTileBytes / 2;
-constexpr int kAttnThreads = 320;
-constexpr int kAttnSmemBytes = 2 * kTileBytes + kNumSlots * kTileBytes + 1024;  // + alignment slack
+constexpr int kSoftmaxWarps = 16;                  // 2 tiles x 2 column halves x 4 row quarters
+constexpr int kTmaWarp = kSoftmaxWarps;
+constexpr int kMmaWarp = kSoftmaxWarps + 1;
+constexpr int kAttnThreads = (kSoftmaxWarps + 2) * 32;
+#ifndef VB_POLY_GROUPS
+#define VB_POLY_GROUPS 0x22        // groups 1 and 5 of every 8 groups of 4 keys: 1/4 of the exps on the FMA pipe (measured best of 0..5/8)
+#endif
+constexpr unsigned kPolyGroups = VB_POLY_GROUPS;
 constexpr float kRescaleThreshold = 8.0f;          // lazy rescale: tolerate 2^8 growth before touching O
+
+struct SmemLayout {
+  uint8_t q[2 * kTileBytes];                 // two query tiles
+  uint8_t kv[kNumSlots * kTileBytes];        // K/V ring
+  uint64_t bar_q_full[2];
+  uint64_t bar_slot_full[kNumSlots];
+  uint64_t bar_slot_empty[kNumSlots];
+  uint64_t bar_s_full[2];
+  uint64_t bar_p_half[2];
+  uint64_t bar_p_ready[2];
+  uint64_t bar_o_full[2];
+  uint32_t tmem_base_slot;
+  KvRun runs[32];
+  float xchg[2][2][kBlockM];                 // row max / row sum exchange between the two threads of a row
+};
+constexpr int kAttnSmemBytes = sizeof(SmemLayout);
+static_assert(kAttnSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 struct BlockWalker {
   const KvRun* runs;
@@ -75,15 +98,20 @@ __device__ __forceinline__ int count_blocks(const KvRun* runs, int n_runs) {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_q_full[2];
-  __shared__ uint64_t bar_slot_full[kNumSlots];
-  __shared__ uint64_t bar_slot_empty[kNumSlots];
-  __shared__ uint64_t bar_s_full[2];
-  __shared__ uint64_t bar_p_ready[2];
-  __shared__ uint64_t bar_o_full[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ KvRun s_runs[32];
+  // Everything lives in dynamic shared memory (no static __shared__), so the operand area starts at the CTA's
+  // shared window base, which is 1024-byte aligned as SWIZZLE_128B needs; checked below.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  uint64_t* bar_q_full = sm.bar_q_full;
+  uint64_t* bar_slot_full = sm.bar_slot_full;
+  uint64_t* bar_slot_empty = sm.bar_slot_empty;
+  uint64_t* bar_s_full = sm.bar_s_full;
+  uint64_t* bar_p_half = sm.bar_p_half;
+  uint64_t* bar_p_ready = sm.bar_p_ready;
+  uint64_t* bar_o_full = sm.bar_o_full;
+  uint32_t& tmem_base_slot = sm.tmem_base_slot;
+  KvRun* s_runs = sm.runs;
+  float (*s_xchg)[2][kBlockM] = sm.xchg;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,10 +120,12 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int batch = blockIdx.z + p.batch0;
   const int nq = pair.nq;
 
-  // 1024-byte aligned operand area (SWIZZLE_128B atoms are 8 rows x 128 B)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;                       // 2 x 32 KB
-  uint8_t* smem_kv = smem + 2 * kTileBytes;     // kNumSlots x 32 KB
+  if ((smem_u32(smem_raw) & 1023u) != 0) {      // SWIZZLE_128B atoms are 8 rows x 128 B
+    if (threadIdx.x == 0) printf("vb_attn_fwd_kernel: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* smem_q = sm.q;                       // 2 x 32 KB
+  uint8_t* smem_kv = sm.kv;                     // kNumSlots x 32 KB
 
   const int n_runs = min(pair.run_count, 32);
   if (threadIdx.x < n_runs) s_runs[threadIdx.x] = p.runs[pair.run_begin + threadIdx.x];
@@ -104,7 +134,8 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_q_full[i], 1);
       mbar_init(&bar_s_full[i], 1);
-      mbar_init(&bar_p_ready[i], kBlockM);
+      mbar_init(&bar_p_half[i], kBlockM);    // 4 warps: column half 0 of P stored
+      mbar_init(&bar_p_ready[i], kBlockM);   // 4 warps: column half 1 of P stored
       mbar_init(&bar_o_full[i], 1);
     }
     for (int i = 0; i < kNumSlots; ++i) {
@@ -113,12 +144,12 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&tmem_base_slot, 512);
     tmem_relinquish();
   }
@@ -128,7 +159,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = tmem_base_slot;
   const int n_blocks = count_blocks(s_runs, n_runs);
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       for (int t = 0; t < nq; ++t) {
@@ -154,7 +185,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =========================================
     // The whole warp runs this role converged and every address below is made warp-uniform, so descriptors live
     // in uniform registers and one elected lane issues; a single-lane role pays a register->uniform "waterfall"
@@ -183,12 +214,14 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           umma_ss(d, desc_hi | (a0 + off), desc_hi | (b0 + off), idesc_qk, k > 0);
         }
       };
-      auto issue_pv = [&](int t, uint32_t slot, uint32_t accumulate) {
+      // PV in two halves of 64 keys, so the first can start as soon as half of P is in TMEM
+      auto issue_pv = [&](int t, uint32_t slot, uint32_t accumulate, int half) {
         const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_v;
         const uint32_t d = tb + 2 * kBlockN + t * kHeadDim;
         const uint32_t a = tb + t * kBlockN;            // P_t: packed bf16 pairs, 8 columns per 16 keys
 #pragma unroll
-        for (int k = 0; k < kBlockN / 16; ++k) {
+        for (int kk = 0; kk < kBlockN / 32; ++kk) {
+          const int k = half * (kBlockN / 32) + kk;
           // V block [128 keys][128 channels], MN-major: 16 keys = 16 rows x 128 B = 2048 B
           umma_ts(d, a + k * 8, desc_hi | (b0 + k * (2048 >> 4)), idesc_pv, accumulate | (k > 0));
         }
@@ -215,12 +248,16 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(&bar_slot_full[v_slot], v_phase);
         if (more) mbar_wait(&bar_slot_full[k_slot], k_phase);
         for (int t = 0; t < nq_u; ++t) {
-          mbar_wait(&bar_p_ready[t], j & 1);
+          mbar_wait(&bar_p_half[t], j & 1);
           if (lane == 0) VB_STAMP(2 + t, j, 0);
+          tc_fence_after();
+          if (elect_one()) issue_pv(t, v_slot, j > 0, 0);
+          __syncwarp();
+          mbar_wait(&bar_p_ready[t], j & 1);
           tc_fence_after();
           if (lane == 0) VB_STAMP(2 + t, j, 1);
           if (elect_one()) {
-            issue_pv(t, v_slot, j > 0);
+            issue_pv(t, v_slot, j > 0, 1);
             if (more) {
               issue_qk(t, k_slot);
               umma_commit(&bar_s_full[t]);
@@ -239,52 +276,58 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else {
     // ============================ softmax / correction / epilogue ===============================
-    const int t = warp >> 2;                         // query tile of this warpgroup
-    const int row = ((warp & 3) << 5) + lane;        // query row inside the tile == TMEM lane
+    // TWO threads per query row: warp = 8 t + 4 h + q handles rows [32 q, 32 q + 32) of tile t, keys / channels
+    // [64 h, 64 h + 64).  All warps with the same q sit on scheduler q and may touch TMEM lanes 32 q..32 q + 31, so
+    // the pair (h = 0, 1) interleaves on one scheduler: a single warp per tile left the issue slot idle ~60 % of the
+    // time on fixed-latency dependencies (round-1 timeline: 1550-1700 cycles per block for ~600 instructions).
+    const int t = warp >> 3;
+    const int h = (warp >> 2) & 1;
+    const int q4 = warp & 3;
+    const int row = (q4 << 5) + lane;               // query row inside the tile == TMEM lane
+    const int pair_bar = 1 + t * 4 + q4;            // named barrier of the two warps sharing these rows
     if (t < nq && n_blocks > 0) {
-      const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) << 5) << 16;
+      const uint32_t lane_addr = static_cast<uint32_t>(q4 << 5) << 16;
       const uint32_t s_addr = tmem_base + lane_addr + t * kBlockN;
-      const uint32_t o_addr = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim;
+      const uint32_t o_addr = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim + h * 64;
       const float scale = p.scale_log2;
       float m_ref = 0.f, l_sum = 0.f;
 
       BlockWalker w(s_runs, n_runs);
       int row0, valid;
       for (int j = 0; w.next(row0, valid); ++j) {
-        if (row == 0) VB_STAMP(t, j, 0);
+        if (row == 0 && h == 0) VB_STAMP(t, j, 0);
         mbar_wait(&bar_s_full[t], j & 1);
         tc_fence_after();
-        if (row == 0) VB_STAMP(t, j, 1);
+        if (row == 0 && h == 0) VB_STAMP(t, j, 1);
 #ifdef VB_EXP_SKIP_SOFTMAX   // perf experiment: tensor-pipe-only throughput (results are garbage)
         tc_fence_before();
-        mbar_arrive(&bar_p_ready[t]);
+        mbar_arrive(h == 0 ? &bar_p_half[t] : &bar_p_ready[t]);
         continue;
 #endif
-        uint32_t s[4][32];
+        uint32_t s[2][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, s[c]);
+        for (int c = 0; c < 2; ++c) tmem_ld32(s_addr + h * 64 + c * 32, s[c]);
         tmem_ld_wait();
-        if (row == 0) VB_STAMP(t, j, 2);
+        if (row == 0 && h == 0) VB_STAMP(t, j, 2);
 #ifndef VB_TIMELINE
         if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-          float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN;   // raw scores of block 0
+          float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN + h * 64;   // raw scores of block 0
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(s[c][i]);
         }
 #endif
-
         if (valid < kBlockN) {   // run tail: keys beyond the run do not exist for this query
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) s[c][i] = 0xff800000u;   // -inf
+              if (h * 64 + c * 32 + i >= valid) s[c][i] = 0xff800000u;   // -inf
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             mx0 = fmaxf(mx0, __uint_as_float(s[c][i + 0]));
@@ -292,66 +335,81 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
             mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
           }
-        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;   // valid >= 1, so finite
+        // row maximum over both halves; the barrier also orders "both threads hold their S values in registers"
+        // before either overwrites S with P
+        s_xchg[t][h][row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        named_bar_sync(pair_bar, 64);
+        const float m_new = fmaxf(s_xchg[t][0][row], s_xchg[t][1][row]) * scale;   // block has >= 1 valid key: finite
+        if (row == 0 && h == 0) VB_STAMP(t, j, 6);
 
-        float alpha = 1.f;
-        bool rescale = false;
         if (j == 0) {
           m_ref = m_new;
         } else {
           const bool need = m_new > m_ref + kRescaleThreshold;
-          rescale = __any_sync(0xffffffffu, need);       // tcgen05.ld/st below are warp-collective
-          if (need) {
-            alpha = fast_exp2(m_ref - m_new);
-            m_ref = m_new;
-          }
-        }
-        l_sum *= alpha;
-
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = hp * 2 + cc;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float e0 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 0]), scale, -m_ref));
-              const float e1 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 1]), scale, -m_ref));
-              const float e2 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 2]), scale, -m_ref));
-              const float e3 = VB_EXP2(fmaf(__uint_as_float(s[c][i + 3]), scale, -m_ref));
-              sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
-              pk[cc * 16 + (i >> 1) + 0] = pack_bf16x2(e0, e1);
-              pk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
+          if (__any_sync(0xffffffffu, need)) {             // identical in both warps of the pair (same rows)
+            float alpha = 1.f;
+            if (need) {
+              alpha = fast_exp2(m_ref - m_new);
+              m_ref = m_new;
             }
+            // PV_t(j-1) completed before S_t(j) was signalled (commit order) and PV_t(j) waits for BOTH halves'
+            // arrivals: O_t is quiescent.  Each thread rescales its 64 channels.
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[16];
+              tmem_ld16(o_addr + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(o_addr + c * 16, o);
+            }
+            l_sum *= alpha;
+            tmem_st_wait();
+            named_bar_sync(pair_bar, 64);    // the half-0 arrive below releases PV over ALL channels
           }
-          tmem_st32(s_addr + hp * 32, pk);   // P_t(j): keys [64 hp, 64 hp + 64) -> 32 columns of bf16 pairs
         }
-        l_sum += (sum0 + sum1) + (sum2 + sum3);
-        if (row == 0) VB_STAMP(t, j, 3);
 
-        if (rescale) {
-          // PV_t(j-1) completed before S_t(j) was signalled (commit order), PV_t(j) waits for our arrive:
-          // O_t is quiescent here.
+        // p = exp2(s * scale - m_ref): packed fp32x2 FMA / ADD (one issue slot per two keys), MUFU ex2 per key
+        const float neg_m = -m_ref;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        uint32_t pk[32];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(o_addr + c * 32, o);
-            tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_addr + c * 32, o);
+          for (int i = 0; i < 32; i += 4) {
+            float x0, x1, x2, x3;
+            ffma2(x0, x1, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]), scale, scale, neg_m, neg_m);
+            ffma2(x2, x3, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]), scale, scale, neg_m, neg_m);
+            float e0, e1, e2, e3;
+            if ((kPolyGroups >> (i >> 2)) & 1) {      // compile-time pattern: this group of 4 keys skips the MUFU
+              exp2_poly2(x0, x1, e0, e1);
+              exp2_poly2(x2, x3, e2, e3);
+            } else {
+              e0 = VB_EXP2(x0); e1 = VB_EXP2(x1); e2 = VB_EXP2(x2); e3 = VB_EXP2(x3);
+            }
+            fadd2(sum0, sum1, sum0, sum1, e0, e1);
+            fadd2(sum2, sum3, sum2, sum3, e2, e3);
+            pk[c * 16 + (i >> 1) + 0] = pack_bf16x2(e0, e1);
+            pk[c * 16 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
           }
+#ifdef VB_TIMELINE
+          if (c == 0) { asm volatile("" ::: "memory"); if (row == 0 && h == 0) VB_STAMP(t, j, 7); }
+#endif
         }
+        tmem_st32(s_addr + h * 32, pk);   // P_t(j): keys [64 h, 64 h + 64) -> 32 columns of bf16 pairs
+        l_sum += (sum0 + sum1) + (sum2 + sum3);
+        if (row == 0 && h == 0) VB_STAMP(t, j, 3);
         tmem_st_wait();
-        if (row == 0) VB_STAMP(t, j, 4);
+        if (row == 0 && h == 0) VB_STAMP(t, j, 4);
         tc_fence_before();
-        mbar_arrive(&bar_p_ready[t]);
-        if (row == 0) VB_STAMP(t, j, 5);
+        mbar_arrive(h == 0 ? &bar_p_half[t] : &bar_p_ready[t]);   // PV over keys [0,64) / [64,128) may start
+        if (row == 0 && h == 0) VB_STAMP(t, j, 5);
       }
 
       // ------------------------------------ epilogue ------------------------------------
+      s_xchg[t][h][row] = l_sum;
+      named_bar_sync(pair_bar, 64);
+      l_sum = s_xchg[t][0][row] + s_xchg[t][1][row];
       mbar_wait(&bar_o_full[t], 0);
       tc_fence_after();
       const bool row_ok = row < pair.q_rows[t];
@@ -370,30 +428,30 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           n_dst += p.bcast_n;
         }
       }
-      __nv_bfloat16* out_head = p.out + batch * p.out_stride_b + head.ho * p.out_stride_h;
+      __nv_bfloat16* out_head = p.out + batch * p.out_stride_b + head.ho * p.out_stride_h + h * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tmem_ld32(o_addr + c * 32, o);
         tmem_ld_wait();
 #ifndef VB_TIMELINE
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-          float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim;
+          float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim + h * 64;
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(o[i]);   // un-normalised O
-          if (c == 0) p.dbg[4 * kBlockM * kBlockN + t * kBlockM + row] = l_sum;
+          if (c == 0 && h == 0) p.dbg[4 * kBlockM * kBlockN + t * kBlockM + row] = l_sum;
         }
 #endif
         for (int dsti = 0; dsti < n_dst; ++dsti) {
           const int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
           uint4* dst = reinterpret_cast<uint4*>(out_head + tok * p.out_stride_s + c * 32);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
+          for (int q4i = 0; q4i < 4; ++q4i) {
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q4 * 8 + i]) * inv;
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q4i * 8 + i]) * inv;
             if (accumulate) {
-              const uint4 prev = dst[q4];
+              const uint4 prev = dst[q4i];
               const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -406,7 +464,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             v.y = pack_bf16x2(f[2], f[3]);
             v.z = pack_bf16x2(f[4], f[5]);
             v.w = pack_bf16x2(f[6], f[7]);
-            dst[q4] = v;
+            dst[q4i] = v;
           }
         }
       }
@@ -415,7 +473,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
