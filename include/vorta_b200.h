@@ -169,6 +169,13 @@ typedef struct {
   void* workspace;
   int64_t workspace_bytes;
   float* debug; /* bring-up only; NULL in production */
+  /* Fused Ulysses "out" exchange over NVLink peer memory (top-1 mode only): when out_peer_count > 0, `out` is
+   * ignored and the output row of token tok is stored into out_peer_ptrs[tok / out_peer_rows] at local token
+   * tok % out_peer_rows, using out_stride as the strides of ONE peer buffer.  The pointers are peer-mapped device
+   * addresses of every rank's receive buffer (this rank's own included). */
+  void* out_peer_ptrs[8];
+  int32_t out_peer_count;
+  int32_t out_peer_rows;
 } vb_attn_args;
 
 int64_t vb_attn_workspace_bytes(const vb_plan* plan, int32_t batch, int32_t heads);
@@ -226,6 +233,12 @@ int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t head
  * ulysses/utils.py:68-74,89). */
 int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s, const int64_t* stride_h,
                         void* send, int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream);
+/* Fused Ulysses "in" exchange over NVLink peer memory: rank `rank` stores heads [p*H/P, (p+1)*H/P) of its S_loc
+ * tokens of q, k, v straight into peer p's receive buffer peer_qkv[p], laid out (3, rows_total, H/P, 128) with
+ * this rank's tokens at rows [rank*S_loc, (rank+1)*S_loc).  Replaces pack + all-to-all (ulysses/utils.py:60-81). */
+int vb_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                           const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
+                           int32_t heads, int32_t world, int32_t rank, vb_stream_t stream);
 int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
                             vb_stream_t stream);
 

@@ -82,6 +82,10 @@ def main():
         v, t = hev(hattn, mine, ehs, mask, rope, routing_score=score, tau_sparse=0.3, **kw)
         check("hunyuan single-stream eval (video)", all_gather(v, dim=1), ref_v)
         check("hunyuan single-stream eval (text)", t, ref_t)
+    from vorta_b200.ulysses import peer
+    if rank == 0:
+        print("exchange:", os.environ.get("VB_ULYSSES", "peer"), "| peer disabled reason:", peer.disabled_reason(),
+              "| peer exchanges built:", len(peer._EXCHANGES), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -426,6 +426,44 @@ def test_full_size_properties_wan13():
     assert_attn_close(out[:, 1:2], ref)
 
 
+def test_full_size_properties_hunyuan_with_text():
+    """HunyuanVideo 720p x 129 f (BASELINE configs[3]): 33x45x80 = 118,800 video tokens + 256 text tokens (64 valid),
+    one head per branch (the grid is what matters; 24 heads only repeat it)."""
+    lat, tile, win, lw, TL, TV = (33, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 256, 64
+    plan = ops.Plan(lat, tile, win, lw, 0.5, text_len=TL, text_valid=TV)
+    S, H = plan.seq_len, 3
+    g = torch.Generator().manual_seed(13)
+    q, k, v = (torch.randn((1, S + TL, H, 128), generator=g).to(torch.bfloat16).to(dev()).transpose(1, 2)
+               for _ in range(3))
+    out = ops.routed_attention(plan, q, k, v, branch=[0, 1, 2], flags=L.ATTN_CORESET_KV_FROM_K)
+    assert torch.isfinite(out.float()).all()
+    assert out[:, :, S + TV:].float().abs().max().item() == 0.0            # padded text queries -> exactly zero
+    ones = torch.ones_like(v)
+    o1 = ops.routed_attention(plan, q, k, ones, branch=[0, 1, 2], flags=L.ATTN_CORESET_KV_FROM_K)
+    assert (o1[:, :, :S + TV].float() - 1).abs().max().item() <= 8e-3      # softmax rows sum to one everywhere
+    qc, kc, vc = q.float().cpu(), k.float().cpu(), v.float().cpu()
+    nv = S + TV
+    # full head: sampled video rows and every valid text row against the fp32 oracle
+    rows = torch.cat([torch.arange(0, S, 1201), torch.arange(S, nv)])
+    assert_attn_close(out[:, 0:1, rows], O.sdpa(qc[:, 0:1, rows], kc[:, 0:1, :nv], vc[:, 0:1, :nv]))
+    # sliding head: three tiles (window + valid text keys) and the valid text rows (every non-pad key)
+    perm = O.tile_permutation(lat, tile).reshape(-1, plan.tile_tokens)
+    wins = O.tile_windows(lat, win, tile)
+    nt = [lat[d] // tile[d] for d in range(3)]
+    text_keys = torch.arange(S, nv)
+    for t in (0, 131, 274):
+        lo, hi = wins[t, :3], wins[t, 3:]
+        ids = [(a * nt[1] + b) * nt[2] + c for a in range(lo[0], hi[0] + 1) for b in range(lo[1], hi[1] + 1)
+               for c in range(lo[2], hi[2] + 1)]
+        keys = torch.cat([perm[ids].reshape(-1), text_keys])
+        assert_attn_close(out[:, 2:3, perm[t]], O.sdpa(qc[:, 2:3, perm[t]], kc[:, 2:3, keys], vc[:, 2:3, keys]))
+    assert_attn_close(out[:, 2:3, S:nv], O.sdpa(qc[:, 2:3, S:nv], kc[:, 2:3, :nv], vc[:, 2:3, :nv]))
+    # coreset head against the oracle run on the same inputs (K and V pooled with K's matching)
+    info = O.get_group_info(lat, lw, 0.5)
+    ref = O.coreset_attention(qc[:, 1:2], kc[:, 1:2], vc[:, 1:2], info, TL, TV, kv_from_k=True)
+    assert_attn_close(out[:, 1:2], ref)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Ulysses layout kernels (single GPU: P ranks emulated as one batch of buffers)
 # ---------------------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "vb_attn_workspace_bytes", "vb_attn_fwd", "vb_attn_dense",
     "vb_block_ln_modulate", "vb_block_gate_residual", "vb_block_rmsnorm_rope",
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
-    "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_unpack_heads",
+    "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_scatter_qkv", "vb_ulysses_unpack_heads",
 )
 
 
@@ -65,6 +65,9 @@ class AttnArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
         ("debug", C.c_void_p),
+        ("out_peer_ptrs", C.c_void_p * 8),
+        ("out_peer_count", C.c_int32),
+        ("out_peer_rows", C.c_int32),
     ]
 
 
@@ -134,6 +137,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp]
     lib.vb_ulysses_pack_qkv.restype = C.c_int
     lib.vb_ulysses_pack_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i32, i32, i32, vp]
+    lib.vb_ulysses_scatter_qkv.restype = C.c_int
+    lib.vb_ulysses_scatter_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32, i32, i32, i32, vp]
     lib.vb_ulysses_unpack_heads.restype = C.c_int
     lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, vp]
 

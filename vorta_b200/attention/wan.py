@@ -21,6 +21,7 @@ import torch
 from .. import _lib as L
 from .. import ops
 from ..ulysses import SP_STATE, exchange_out, exchange_qkv, local_heads, shrink_dim
+from ..ulysses.peer import get_exchange
 from ._plans import get_plan, infer_lowres_window
 from .coreset_select import LowresGroupInfo
 
@@ -170,18 +171,25 @@ class WanAttnProcessorTripleTrain(WanAttnProcessor2_0):
     def _routed_attention(self, query, key, value, plan: ops.Plan, branch=None, weights=None) -> torch.Tensor:
         """All branches of one layer: a single C-ABI call between the two Ulysses exchanges."""
         heads = query.shape[1]
-        if SP_STATE.enabled:
-            query, key, value = exchange_qkv(query, key, value)
-            if branch is not None:
-                branch = local_heads(list(branch), heads)
-            if weights is not None:
-                hp = heads // SP_STATE.sp_size
-                r = SP_STATE.group_local_rank
-                weights = weights[:, r * hp:(r + 1) * hp]
+        if not SP_STATE.enabled:
+            return ops.routed_attention(plan, query, key, value, branch=branch, weights=weights)
+        hp = heads // SP_STATE.sp_size
+        r = SP_STATE.group_local_rank
+        if branch is not None:
+            branch = local_heads(list(branch), heads)
+        if weights is not None:
+            weights = weights[:, r * hp:(r + 1) * hp]
+        ex = get_exchange(heads, query.shape[2], query.device) if (weights is None and query.shape[0] == 1) else None
+        if ex is not None:
+            # NVLink peer-memory path: Q/K/V rows are stored straight into the owner ranks' buffers, and the attention
+            # epilogue stores every output row straight into the buffer of the rank that owns the token
+            q, k, v = ex.scatter_qkv(query, key, value)
+            ops.routed_attention(plan, q, k, v, branch=branch, out_peers=ex.out_ptrs, out_peer_rows=ex.s_loc,
+                                 out_peer_strides=(0, 128, heads * 128), head_offset=r * hp)
+            return ex.finish_out()
+        query, key, value = exchange_qkv(query, key, value)
         out = ops.routed_attention(plan, query, key, value, branch=branch, weights=weights)
-        if SP_STATE.enabled:
-            out = exchange_out(out)
-        return out
+        return exchange_out(out)
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None,

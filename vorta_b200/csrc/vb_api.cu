@@ -48,6 +48,9 @@ int launch_gate_residual(const void* x, const void* y, const float* gate, void* 
                          int rows_per_batch, cudaStream_t stream);
 int launch_rmsnorm_rope(const void* x, const void* weight, const float* cs, const float* sn, void* out, int64_t rows,
                         int dim, int tokens_per_batch, float eps, cudaStream_t stream);
+int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                               const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int heads,
+                               int world, int rank, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
@@ -526,6 +529,10 @@ static int run_branch(const BranchLaunch& bl, const vb_attn_args& a, const std::
     p.out_map = bl.out_map; p.out_map_stride_b = bl.out_map_stride_b; p.out_map_stride_h = bl.out_map_stride_h;
     p.bcast_map = bl.bcast_map; p.bcast_stride_b = bl.bcast_stride_b; p.bcast_stride_h = bl.bcast_stride_h;
     p.bcast_rows = bl.bcast_rows; p.bcast_n = bl.bcast_n;
+    p.out_peer_count = a.out_peer_count;
+    p.out_peer_rows = a.out_peer_rows;
+    for (int i = 0; i < 8; ++i)
+      p.out_peers[i] = i < a.out_peer_count ? static_cast<__nv_bfloat16*>(a.out_peer_ptrs[i]) : nullptr;
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
     p.batch0 = batch0;
     p.dbg = a.debug;
@@ -559,7 +566,10 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   VB_REQUIRE(pl != nullptr && args != nullptr, VB_ERR_INVALID, "null argument");
   VB_REQUIRE(pl->has_device, VB_ERR_UNSUPPORTED, "no CUDA device: vorta_b200 has no CPU path");
   const vb_attn_args& a = *args;
-  VB_REQUIRE(a.q && a.k && a.v && a.out, VB_ERR_INVALID, "null tensor");
+  VB_REQUIRE(a.q && a.k && a.v && (a.out || a.out_peer_count > 0), VB_ERR_INVALID, "null tensor");
+  VB_REQUIRE(a.out_peer_count >= 0 && a.out_peer_count <= 8, VB_ERR_INVALID, "out_peer_count must be within [0, 8]");
+  VB_REQUIRE(a.out_peer_count == 0 || (a.weights == nullptr && a.out_peer_rows > 0 && pl->d.text_len == 0),
+             VB_ERR_UNSUPPORTED, "peer output needs top-1 routing, out_peer_rows > 0 and no text segment");
   VB_REQUIRE(a.batch > 0 && a.heads > 0, VB_ERR_INVALID, "batch and heads must be positive");
   VB_REQUIRE(a.weights != nullptr || a.branch != nullptr, VB_ERR_INVALID, "need branch ids or blend weights");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -852,6 +862,15 @@ int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64
   VB_REQUIRE(q && k && v && send && stride_s && stride_h, VB_ERR_INVALID, "null argument");
   int rc = launch_ulysses_pack_qkv(q, k, v, stride_s, stride_h, send, s_loc, heads, world,
                                    static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                           const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
+                           int32_t heads, int32_t world, int32_t rank, vb_stream_t stream) {
+  VB_REQUIRE(q && k && v && stride_s && stride_h && peer_qkv, VB_ERR_INVALID, "null argument");
+  int rc = launch_ulysses_scatter_qkv(q, k, v, stride_s, stride_h, peer_qkv, rows_total, s_loc, heads, world, rank,
+                                      static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }

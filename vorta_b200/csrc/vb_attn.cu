@@ -428,7 +428,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           n_dst += p.bcast_n;
         }
       }
-      __nv_bfloat16* out_head = p.out + batch * p.out_stride_b + head.ho * p.out_stride_h + h * 64;
+      const int64_t head_off = batch * p.out_stride_b + head.ho * p.out_stride_h + h * 64;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
@@ -443,8 +443,14 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
 #endif
         for (int dsti = 0; dsti < n_dst; ++dsti) {
-          const int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
-          uint4* dst = reinterpret_cast<uint4*>(out_head + tok * p.out_stride_s + c * 32);
+          int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
+          __nv_bfloat16* obase = p.out;
+          if (p.out_peer_count > 0) {      // fused Ulysses "out" exchange: the owner rank of this token gets the row
+            const int peer = static_cast<int>(tok / p.out_peer_rows);
+            obase = p.out_peers[peer];
+            tok -= static_cast<int64_t>(peer) * p.out_peer_rows;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(obase + head_off + tok * p.out_stride_s + c * 32);
 #pragma unroll
           for (int q4i = 0; q4i < 4; ++q4i) {
             float f[8];

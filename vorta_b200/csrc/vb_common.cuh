@@ -63,6 +63,10 @@ struct AttnParams {
   const KvRun* runs;
   __nv_bfloat16* out;
   int64_t out_stride_b, out_stride_h, out_stride_s;   // elements
+  // Ulysses "peer" output: when out_peer_count > 0 token tok belongs to rank tok / out_peer_rows and its row is stored
+  // straight into that rank's buffer over NVLink (out_stride_* then describe ONE peer buffer, token index local)
+  __nv_bfloat16* out_peers[8];
+  int32_t out_peer_count, out_peer_rows;
   const int32_t* out_map;       // kernel row -> output token, nullptr = identity
   int64_t out_map_stride_h;     // per-head stride of out_map (0 = shared by all heads), indexed by hk
   int64_t out_map_stride_b;

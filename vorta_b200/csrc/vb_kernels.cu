@@ -393,6 +393,59 @@ int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const i
   return VB_OK;
 }
 
+struct ScatterQkvParams {
+  const uint4* src[3];
+  int64_t stride_s[3], stride_h[3];
+  uint4* peer[8];
+};
+// Stores every (token, head) row of q, k, v into the receive buffer of the rank that owns the head: the Ulysses "in"
+// exchange as plain NVLink stores (16-byte vectors, 256-byte rows), no staging copy and no collective call.
+__global__ void __launch_bounds__(256)
+vb_ulysses_scatter_qkv_kernel(const ScatterQkvParams p, int64_t rows_total, int s_loc, int heads, int world, int rank) {
+  const int hp = heads / world;
+  const int64_t rows = static_cast<int64_t>(s_loc) * heads;
+  const int64_t total = rows * 3 * 16;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 15);
+    int64_t r = i >> 4;
+    // order (tensor, peer, token, head-in-chunk): consecutive threads walk one peer's rows contiguously
+    const int hh = static_cast<int>(r % hp);
+    r /= hp;
+    const int64_t sidx = r % s_loc;
+    r /= s_loc;
+    const int peer = static_cast<int>(r % world);
+    const int t = static_cast<int>(r / world);
+    const int hsrc = peer * hp + hh;
+    const uint4 val = p.src[t][(sidx * p.stride_s[t] + hsrc * p.stride_h[t]) / 8 + c];
+    const int64_t dst = ((static_cast<int64_t>(t) * rows_total + static_cast<int64_t>(rank) * s_loc + sidx) * hp + hh) * 16 + c;
+    p.peer[peer][dst] = val;
+  }
+}
+
+int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                               const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int heads,
+                               int world, int rank, cudaStream_t stream) {
+  VB_REQUIRE(world > 0 && world <= 8 && heads % world == 0, VB_ERR_INVALID, "heads %d / world %d not supported", heads,
+             world);
+  ScatterQkvParams p;
+  p.src[0] = static_cast<const uint4*>(q);
+  p.src[1] = static_cast<const uint4*>(k);
+  p.src[2] = static_cast<const uint4*>(v);
+  for (int i = 0; i < 3; ++i) {
+    VB_REQUIRE(stride_s[i] % 8 == 0 && stride_h[i] % 8 == 0, VB_ERR_INVALID, "strides must be multiples of 8 elements");
+    p.stride_s[i] = stride_s[i];
+    p.stride_h[i] = stride_h[i];
+  }
+  for (int i = 0; i < 8; ++i) p.peer[i] = i < world ? static_cast<uint4*>(peer_qkv[i]) : nullptr;
+  const int64_t total = static_cast<int64_t>(s_loc) * heads * 3 * 16;
+  if (total == 0) return VB_OK;
+  const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  vb_ulysses_scatter_qkv_kernel<<<grid, 256, 0, stream>>>(p, rows_total, s_loc, heads, world, rank);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
 int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
                            int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream) {
   VB_REQUIRE(world > 0 && heads % world == 0, VB_ERR_INVALID, "heads %d not divisible by world %d", heads, world);

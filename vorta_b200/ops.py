@@ -125,7 +125,9 @@ class Plan:
 def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                      branch: Optional[Sequence[int]] = None, weights: Optional[torch.Tensor] = None,
                      flags: int = 0, out: Optional[torch.Tensor] = None,
-                     debug: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     debug: Optional[torch.Tensor] = None, out_peers: Optional[Sequence[int]] = None,
+                     out_peer_rows: int = 0, out_peer_strides: Optional[Sequence[int]] = None,
+                     head_offset: int = 0) -> Optional[torch.Tensor]:
     """One routed self-attention layer.  q, k, v: (B, H, S + text_len, 128) bf16 views (any batch / head / token
     strides).  ``branch``: per-head VB_BRANCH_* ids (Eval processor semantics, wan.py:388-438); ``weights``:
     (B, H, 3) routing scores for the blended Train semantics (wan.py:296-300).  Returns (B, H, N, 128) as a view
@@ -136,16 +138,28 @@ def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
     if N != plan.seq_len + plan.text_len:
         raise ValueError(f"Input sequence length {N} does not match latent shape {plan.latent_shape}"
                          f" (+ text {plan.text_len}).")
-    if out is None:
-        out = torch.empty((B, N, H, D), dtype=q.dtype, device=q.device).transpose(1, 2)
-    else:
-        _require_cuda_bf16("out", out)
     args = L.AttnArgs()
-    args.q, args.k, args.v, args.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    if out_peers is not None:
+        # fused Ulysses "out" exchange: rows go straight into the owner ranks' (S_loc, H_total, 128) buffers; this
+        # rank's heads start at head_offset there (folded into the base pointers)
+        out = None
+        sb, sh, ss = out_peer_strides
+        args.out = None
+        args.out_stride[:] = (sb, sh, ss)
+        for i, ptr in enumerate(out_peers):
+            args.out_peer_ptrs[i] = int(ptr) + head_offset * sh * 2
+        args.out_peer_count, args.out_peer_rows = len(out_peers), int(out_peer_rows)
+    else:
+        if out is None:
+            out = torch.empty((B, N, H, D), dtype=q.dtype, device=q.device).transpose(1, 2)
+        else:
+            _require_cuda_bf16("out", out)
+        args.out = out.data_ptr()
+        args.out_stride[:] = out.stride()[:3]
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     args.q_stride[:] = q.stride()[:3]
     args.k_stride[:] = k.stride()[:3]
     args.v_stride[:] = v.stride()[:3]
-    args.out_stride[:] = out.stride()[:3]
     args.batch, args.heads = B, H
     keep = []
     if weights is not None:
