@@ -33,6 +33,10 @@ WORKLOADS = {
                   lowres_window=(3, 3, 2), rate=0.5, text_tokens=512,
                   name="Wan2.1-T2V-1.3B 480p x81f (21x30x52 = 32,760 tokens, 12 heads, 30 blocks), one denoise step"),
 }
+WORKLOADS["hunyuan"] = dict(model="hunyuanvideo", latent=(33, 45, 80), tile=(3, 9, 16), window=(3, 3, 3),
+                            lowres_window=(3, 3, 2), rate=0.5, text_tokens=256, text_valid=64,
+                            name="HunyuanVideo 720p x129f (33x45x80 = 118,800 video tokens + 256 text (64 valid), 24 heads, "
+                                 "20 dual + 40 single blocks), one denoise step")
 TAU_SPARSE = 0.3          # the reference's inference default (scripts/wan/inference.py:75)
 
 
@@ -169,6 +173,15 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 def build_model(wl, device):
     import torch
+    if wl["model"] == "hunyuanvideo":
+        from vorta_b200.dit import HunyuanDiT
+        from vorta_b200.patch import modeling_hunyuan, prepare_hunyuan_self_attn_kwargs
+        model = HunyuanDiT.build(wl["model"], device, torch.bfloat16, seed=0)
+        modeling_hunyuan.apply_vorta_transformer(model, train_router=False, router_dtype=torch.float32)
+        kw = prepare_hunyuan_self_attn_kwargs(
+            dict(latent_shape=wl["latent"], window_size=wl["window"], tile_size=wl["tile"],
+                 lowres_window_size=wl["lowres_window"], lowres_reduction_rate=wl["rate"]), device, tau_sparse=TAU_SPARSE)
+        return model, kw
     from vorta_b200.dit import WanDiT
     from vorta_b200.patch import apply_vorta_transformer, prepare_wan_self_attn_kwargs
     model = WanDiT.build(wl["model"], device, torch.bfloat16, seed=0)
@@ -184,9 +197,24 @@ def host_inputs(wl, cfg):
     g = torch.Generator().manual_seed(1234)
     T, H, W = wl["latent"]
     lat = torch.randn((1, cfg.in_channels, T, 2 * H, 2 * W), generator=g).to(torch.bfloat16).pin_memory()
-    txt = torch.randn((1, wl["text_tokens"], cfg.text_dim), generator=g).to(torch.bfloat16).pin_memory()
+    text_dim = cfg.text_embed_dim if hasattr(cfg, "text_embed_dim") else cfg.text_dim
+    txt = torch.randn((1, wl["text_tokens"], text_dim), generator=g).to(torch.bfloat16).pin_memory()
     ts = torch.tensor([500.0]).pin_memory()
     return lat, txt, ts
+
+
+def make_step(model, wl, device, kw):
+    """Returns call(latents, timestep, text) -> model outputs for the workload's model family."""
+    import torch
+    if wl["model"] != "hunyuanvideo":
+        return lambda lat, ts, txt, **extra: model(lat, ts, txt, self_attention_kwargs=kw, **extra)
+    g = torch.Generator().manual_seed(99)
+    mask = torch.zeros((1, wl["text_tokens"]), dtype=torch.bool, device=device)
+    mask[:, :wl["text_valid"]] = True
+    pooled = torch.randn((1, model.config.pooled_projection_dim), generator=g).to(device, torch.bfloat16)
+    guidance = torch.tensor([6000.0], device=device)
+    return lambda lat, ts, txt, **extra: model(lat, ts, txt, mask, pooled, guidance, self_attention_kwargs=dict(kw),
+                                               **extra)
 
 
 def time_steps(fn, steps, warmup, dist_on, profile=False):
@@ -229,22 +257,24 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
     lat_d, txt_d, ts_d = lat_h.to(device), txt_h.to(device), ts_h.to(device)
     out_h = torch.empty(lat_h.shape, dtype=torch.bfloat16).pin_memory()
 
+    call = make_step(model, wl, device, kw)
+
     @torch.no_grad()
     def step_resident():
-        return model(lat_d, ts_d, txt_d, self_attention_kwargs=kw)[0]
+        return call(lat_d, ts_d, txt_d)[0]
 
     @torch.no_grad()
     def step_e2e():
         a = lat_h.to(device, non_blocking=True)
         b = txt_h.to(device, non_blocking=True)
         c = ts_h.to(device, non_blocking=True)
-        out = model(a, c, b, self_attention_kwargs=kw)[0]
+        out = call(a, c, b)[0]
         out_h.copy_(out, non_blocking=True)
         return out
 
     # routing mix of this run (one untimed forward)
     with torch.no_grad():
-        _, scores = model(lat_d, ts_d, txt_d, self_attention_kwargs=kw, return_routing_scores=True)
+        _, scores = call(lat_d, ts_d, txt_d, return_routing_scores=True)
     branches = [s[0].float().argmax(-1).tolist() for s in scores]
     counts = branch_counts(branches)
 
