@@ -132,18 +132,28 @@ def cpu_step_ms(per_head_ms, counts):
     return per_head_ms["full"] * counts[0] + per_head_ms["coreset"] * counts[1] + per_head_ms["sliding"] * counts[2]
 
 
+def model_dims(wl):
+    """(heads, attention layers) of the workload's architecture."""
+    if wl["model"] == "hunyuanvideo":
+        from vorta_b200.dit import HUNYUAN_CONFIGS
+        c = HUNYUAN_CONFIGS[wl["model"]]
+        return c.heads, c.num_layers + c.num_single_layers
+    from vorta_b200.dit import WAN_CONFIGS
+    c = WAN_CONFIGS[wl["model"]]
+    return c.heads, c.num_layers
+
+
 def run_reference(args):
     import torch
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                   # rank 0 alone runs the CPU arm
-    from vorta_b200.dit import WAN_CONFIGS
-    cfg = WAN_CONFIGS[wl["model"]]
+    heads, layers = model_dims(wl)
     cores = torch.get_num_threads()
     # the same head-branch mix the GPU arm reports is unknown here without a GPU: price a uniform 1/3 mix, which
     # is what random-init routers produce in expectation; the GPU arm's line carries its exact counts
-    total_heads = cfg.heads * cfg.num_layers
+    total_heads = heads * layers
     counts = [total_heads / 3.0] * 3
     for _ in range(args.warmup):
         cpu_sample_ms(dict(wl, latent=(3, 9, 16), tile=(3, 9, 16), lowres_window=(3, 3, 2)))   # tiny warm-up
@@ -154,8 +164,8 @@ def run_reference(args):
         steps.append(cpu_step_ms(last, counts))
     value = statistics.mean(steps)
     sample = (f"{args.steps} x (one head per branch: full / coreset / sliding at S={wl['latent'][0] * wl['latent'][1] * wl['latent'][2]}, "
-              f"fp32 torch CPU SDPA, oracle port of the reference path); step = per-head times x {cfg.heads} heads x "
-              f"{cfg.num_layers} layers at a uniform 1/3 branch mix; ATTENTION ONLY (the CPU linears are not timed)")
+              f"fp32 torch CPU SDPA, oracle port of the reference path); step = per-head times x {heads} heads x "
+              f"{layers} layers at a uniform 1/3 branch mix; ATTENTION ONLY (the CPU linears are not timed)")
     line = dict(impl="reference", metric="dit_denoise_step_ms", value=value, unit="ms", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=value, higher_is_better=False, scaling="strong",
                 vs_baseline=None, dtype="f32", data="synthetic",
@@ -359,7 +369,7 @@ def run_gpu(args):
                 per_head_ms=per_head,
                 sample=(f"one head per branch (full / coreset / sliding) at S={S}, fp32 torch CPU SDPA (oracle port of the "
                         f"reference path), timed once; value = per-head ms x this run's head-branch counts over all "
-                        f"{cfg.num_layers} layers; ATTENTION ONLY, the CPU linears are not timed"))
+                        f"{model_dims(wl)[1]} layers; ATTENTION ONLY, the CPU linears are not timed"))
         if args.workload == "wan14" and not args.no_aux:
             a = run_workload(WORKLOADS["wan13"], args, rank, world, device, with_e2e=True)
             ach = a["attn_flops_step"] / (a["attn_ms_step"] * 1e-3) / 1e12
