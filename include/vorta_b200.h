@@ -176,6 +176,10 @@ typedef struct {
   void* out_peer_ptrs[8];
   int32_t out_peer_count;
   int32_t out_peer_rows;
+  /* Optional (host pointer, heads entries, or NULL = identity): head index along `out`'s head stride that receives
+   * the output of local head h.  Lets a rank that holds an arbitrary, cost-balanced subset of the layer's heads
+   * (Ulysses) write each head where the token owner expects it. */
+  const int32_t* out_heads;
 } vb_attn_args;
 
 int64_t vb_attn_workspace_bytes(const vb_plan* plan, int32_t batch, int32_t heads);
@@ -225,22 +229,30 @@ int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops);
  *   unpack: recv (P, S_loc, H/P, 128)     -> y (S_loc, H, 128)
  * The receive buffer of the "in" direction, (P*S_loc, H/P, 128), and the send buffer of the "out" direction are
  * consumed / produced by vb_attn_fwd directly through its strides, so each direction needs one pass only.
+ *
+ * head_at (host pointer, H entries, or NULL): slot p*H/P + i of the exchanged layout holds head head_at[p*H/P + i].
+ * NULL is the reference's contiguous chunking (ulysses/utils.py:60-66).  Because every rank knows the whole step's
+ * routing before the first block runs, the host can pass a permutation that balances the per-rank attention cost
+ * (full : coreset : sliding heads differ ~ 6 : 1.6 : 1); it must be a permutation of [0, H), H <= 128, identical on
+ * every rank and for the pack and unpack sides of one layer.
  * ---------------------------------------------------------------------------------------------------- */
 int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t heads, int32_t world, int32_t n_tensors,
-                          int64_t x_tensor_stride, int64_t send_tensor_stride, vb_stream_t stream);
+                          int64_t x_tensor_stride, int64_t send_tensor_stride, const int32_t* head_at,
+                          vb_stream_t stream);
 /* q, k, v: (S_loc, H, 128), each with its own element strides stride_s[3] (token) / stride_h[3] (head) ->
  * send (3, P, S_loc, H/P, 128) in one pass (the reference makes two transposed copies per tensor,
  * ulysses/utils.py:68-74,89). */
 int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s, const int64_t* stride_h,
-                        void* send, int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream);
-/* Fused Ulysses "in" exchange over NVLink peer memory: rank `rank` stores heads [p*H/P, (p+1)*H/P) of its S_loc
+                        void* send, int32_t s_loc, int32_t heads, int32_t world, const int32_t* head_at,
+                        vb_stream_t stream);
+/* Fused Ulysses "in" exchange over NVLink peer memory: rank `rank` stores the heads of slots [p*H/P, (p+1)*H/P) of its S_loc
  * tokens of q, k, v straight into peer p's receive buffer peer_qkv[p], laid out (3, rows_total, H/P, 128) with
  * this rank's tokens at rows [rank*S_loc, (rank+1)*S_loc).  Replaces pack + all-to-all (ulysses/utils.py:60-81). */
 int vb_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                            const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
-                           int32_t heads, int32_t world, int32_t rank, vb_stream_t stream);
+                           int32_t heads, int32_t world, int32_t rank, const int32_t* head_at, vb_stream_t stream);
 int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
-                            vb_stream_t stream);
+                            const int32_t* head_at, vb_stream_t stream);
 
 #ifdef __cplusplus
 }

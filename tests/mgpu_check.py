@@ -82,10 +82,13 @@ def main():
         v, t = hev(hattn, mine, ehs, mask, rope, routing_score=score, tau_sparse=0.3, **kw)
         check("hunyuan single-stream eval (video)", all_gather(v, dim=1), ref_v)
         check("hunyuan single-stream eval (text)", t, ref_t)
-    from vorta_b200.ulysses import peer
+    from vorta_b200.ulysses import balance, peer
+    from vorta_b200.attention.wan import _top1_branches
     if rank == 0:
+        br = _top1_branches(score, 0.3)
         print("exchange:", os.environ.get("VB_ULYSSES", "peer"), "| peer disabled reason:", peer.disabled_reason(),
-              "| peer exchanges built:", len(peer._EXCHANGES), flush=True)
+              "| peer exchanges built:", len(peer._EXCHANGES), "| head balancing:", balance.enabled(),
+              "| branches:", br, "| head_at:", balance.balance_heads(br, [6.0, 1.6, 1.0], world), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

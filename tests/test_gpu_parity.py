@@ -488,3 +488,51 @@ def test_ulysses_pack_unpack_kernels():
         recv = torch.stack([outs[p][r] for p in range(P)])
         y = unpack_heads(recv)                                    # (S_loc, H, D)
         assert torch.equal(y.unsqueeze(0).transpose(1, 2).cpu(), shards[r])
+
+
+def test_ulysses_pack_unpack_with_balanced_head_table():
+    """A slot -> head table only renumbers heads inside the exchange: rank r receives heads head_at[r*hp:(r+1)*hp]
+    over the full sequence, and the unpack side returns every head to its own index."""
+    from vorta_b200.ulysses import balance_heads, pack_heads, unpack_heads
+    P, s_loc, H = 4, 24, 8
+    branch = [0, 0, 0, 1, 2, 2, 1, 0]
+    head_at = balance_heads(branch, [6.0, 1.6, 1.0], P)
+    assert head_at is not None and sorted(head_at) == list(range(H)) and head_at != list(range(H))
+    hp = H // P
+    g = torch.Generator().manual_seed(3)
+    shards = [torch.randn((1, H, s_loc, 128), generator=g).to(torch.bfloat16) for _ in range(P)]
+    full = torch.cat(shards, dim=2)                               # (1, H, S, D)
+    sends = []
+    for r in range(P):
+        x = shards[r].transpose(1, 2).reshape(1, s_loc, H, 128).contiguous().to(dev())
+        sends.append(pack_heads(x, P, head_at)[0])
+    outs = []
+    for r in range(P):
+        recv = torch.stack([sends[p][r] for p in range(P)])
+        got = recv.reshape(P * s_loc, hp, 128).unsqueeze(0).transpose(1, 2)
+        assert torch.equal(got.cpu(), full[:, head_at[r * hp:(r + 1) * hp]])
+        outs.append(got.transpose(1, 2).reshape(P, s_loc, hp, 128).contiguous())
+    for r in range(P):
+        recv = torch.stack([outs[p][r] for p in range(P)])
+        y = unpack_heads(recv, head_at)
+        assert torch.equal(y.unsqueeze(0).transpose(1, 2).cpu(), shards[r])
+    with pytest.raises(L.VortaB200Error):
+        pack_heads(x, P, [0] * H)                                 # not a permutation
+
+
+def test_out_heads_places_local_heads_in_a_wider_output():
+    """vb_attn_args.out_heads: a rank holding heads {5, 1, 6} of an 8-head layer writes them at those indices."""
+    lat, tile, win, lw = (4, 6, 8), (2, 3, 4), (3, 3, 3), (2, 3, 2)
+    S, H_all, mine = 192, 8, [5, 1, 6]
+    g = torch.Generator().manual_seed(4)
+    q, k, v = (torch.randn((1, H_all, S, 128), generator=g).to(torch.bfloat16).to(dev()) for _ in range(3))
+    branch = [0, 1, 2, 0, 1, 2, 0, 1]
+    plan = ops.Plan(lat, tile, win, lw, 0.5)
+    ref = ops.routed_attention(plan, q, k, v, branch=branch)
+    out = torch.zeros((1, S, H_all, 128), dtype=torch.bfloat16, device=dev()).transpose(1, 2)
+    ops.routed_attention(plan, q[:, mine], k[:, mine], v[:, mine], branch=[branch[h] for h in mine], out=out,
+                         out_heads=mine)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, mine], ref[:, mine])
+    rest = [h for h in range(H_all) if h not in mine]
+    assert out[:, rest].abs().max().item() == 0

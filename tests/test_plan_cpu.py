@@ -111,3 +111,35 @@ def test_prepare_kwargs_mirror_reference_keys():
         wan_pixel2token((78, 720, 1280))
     sched = create_sliding_tile_attn_mask_func((4, 6, 8), (3, 3, 3), (2, 3, 4), 0, 0)
     assert sched.tile_windows().shape == (8, 6)
+
+
+def test_balance_heads_is_a_valid_and_better_placement():
+    """Cost-balanced Ulysses head placement (vorta_b200/ulysses/balance.py): a permutation with H/P heads per rank,
+    never worse than the reference's contiguous chunks, deterministic, identity -> None."""
+    import random
+    from vorta_b200.ulysses import balance_heads
+    costs = [2.93, 0.73, 0.45]          # Wan-14B 720p TFLOP per head: full / coreset / sliding (SURVEY.md 8d)
+    rng = random.Random(7)
+    worse = 0
+    for world in (2, 4, 8):
+        for _ in range(200):
+            H = 40
+            branch = [rng.choice([0, 1, 2]) for _ in range(H)]
+            hp = H // world
+            head_at = balance_heads(branch, costs, world)
+            contiguous = max(sum(costs[e] for e in branch[r * hp:(r + 1) * hp]) for r in range(world))
+            if head_at is None:
+                continue
+            assert sorted(head_at) == list(range(H))
+            assert head_at == balance_heads(list(branch), costs, world)
+            for r in range(world):
+                chunk = head_at[r * hp:(r + 1) * hp]
+                assert chunk == sorted(chunk)
+            load = max(sum(costs[branch[h]] for h in head_at[r * hp:(r + 1) * hp]) for r in range(world))
+            assert load < contiguous
+            ideal = sum(costs[e] for e in branch) / world
+            worse += load > 1.35 * ideal
+    assert worse == 0                                      # LPT stays close to the ideal split on this cost mix
+    assert balance_heads([0] * 8, costs, 4) is None        # uniform routing: contiguous is already optimal
+    assert balance_heads([0, 1, 2], costs, 1) is None
+    assert balance_heads([0, 1, 2], costs, 2) is None      # heads not divisible: left to the caller's error path

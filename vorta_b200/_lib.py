@@ -68,6 +68,7 @@ class AttnArgs(C.Structure):
         ("out_peer_ptrs", C.c_void_p * 8),
         ("out_peer_count", C.c_int32),
         ("out_peer_rows", C.c_int32),
+        ("out_heads", C.POINTER(C.c_int32)),
     ]
 
 
@@ -134,13 +135,14 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_timing_collect.restype = C.c_int
     lib.vb_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb_ulysses_pack_heads.restype = C.c_int
-    lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp]
+    lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, C.POINTER(i32), vp]
     lib.vb_ulysses_pack_qkv.restype = C.c_int
-    lib.vb_ulysses_pack_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i32, i32, i32, vp]
+    lib.vb_ulysses_pack_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i32, i32, i32, C.POINTER(i32), vp]
     lib.vb_ulysses_scatter_qkv.restype = C.c_int
-    lib.vb_ulysses_scatter_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32, i32, i32, i32, vp]
+    lib.vb_ulysses_scatter_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32, i32, i32, i32,
+                                           C.POINTER(i32), vp]
     lib.vb_ulysses_unpack_heads.restype = C.c_int
-    lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, C.POINTER(i32), vp]
 
 
 def lib() -> C.CDLL:

@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib as L
 from .. import ops
-from ..ulysses import SP_STATE, all_gather, exchange_out, exchange_qkv, local_heads, shrink_dim
+from ..ulysses import SP_STATE, all_gather, balance, exchange_out, exchange_qkv, local_heads, shrink_dim
 from ._plans import get_plan, infer_lowres_window
 from .coreset_select import LowresGroupInfo
 from .wan import _top1_branches
@@ -89,21 +89,35 @@ class HunyuanVideoFlashAttnProcessor:
         replicated text tokens and the text outputs are all-gathered over heads (hunyuan.py:147-164,184-187)."""
         B, H = query.shape[:2]
         assert B == 1, f"Batch size {B} is not supported for {self.__class__.__name__}."        # hunyuan.py:168
+        head_at = None
         if SP_STATE.enabled:
+            P, r = SP_STATE.sp_size, SP_STATE.group_local_rank
+            hp = H // P
+            if branch is not None and balance.enabled():      # cost-balanced head placement (SURVEY.md section 8e)
+                head_at = balance.balance_heads(list(branch), balance.branch_costs(plan), P)
             qv, kv, vv = exchange_qkv(query[:, :, :-text_len], key[:, :, :-text_len], value[:, :, :-text_len],
-                                      extra_rows=text_len)
+                                      extra_rows=text_len, head_at=head_at)
+            mine = None
+            if head_at is not None:
+                mine = torch.tensor(head_at[r * hp:(r + 1) * hp], device=query.device)
             for full, src in ((qv, query), (kv, key), (vv, value)):
-                full[:, :, -text_len:] = shrink_dim(src[:, :, -text_len:], dim=1)
+                # replicated text tokens: this rank's heads (hunyuan.py:151-153 shrink_dim over heads)
+                full[:, :, -text_len:] = (shrink_dim(src[:, :, -text_len:], dim=1) if mine is None
+                                          else src[:, :, -text_len:].index_select(1, mine))
             query, key, value = qv, kv, vv
             if branch is not None:
-                branch = local_heads(list(branch), H)
+                branch = local_heads(list(branch), H, head_at)
             if weights is not None:
                 weights = shrink_dim(weights, dim=1)
         out = ops.routed_attention(plan, query, key, value, branch=branch, weights=weights, flags=flags)
         video, text = out[:, :, :-text_len], out[:, :, -text_len:]
         if SP_STATE.enabled:
-            video = exchange_out(video)
+            video = exchange_out(video, head_at)
             text = all_gather(text.contiguous(), dim=1)
+            if head_at is not None:       # gathered in slot order: put every head back at its own index
+                inverse = torch.empty(H, dtype=torch.long)
+                inverse[torch.tensor(head_at)] = torch.arange(H)
+                text = text.index_select(1, inverse.to(text.device))
         return video, text
 
     def _step_attention(self, query, key, value, attention_mask, encoder_hidden_states_seq_len: int,

@@ -20,7 +20,7 @@ import torch
 
 from .. import _lib as L
 from .. import ops
-from ..ulysses import SP_STATE, exchange_out, exchange_qkv, local_heads, shrink_dim
+from ..ulysses import SP_STATE, balance, exchange_out, exchange_qkv, local_heads, shrink_dim
 from ..ulysses.peer import get_exchange
 from ._plans import get_plan, infer_lowres_window
 from .coreset_select import LowresGroupInfo
@@ -175,21 +175,27 @@ class WanAttnProcessorTripleTrain(WanAttnProcessor2_0):
             return ops.routed_attention(plan, query, key, value, branch=branch, weights=weights)
         hp = heads // SP_STATE.sp_size
         r = SP_STATE.group_local_rank
+        head_at = None
         if branch is not None:
-            branch = local_heads(list(branch), heads)
+            # the routing of the layer is known on every rank: hand each rank a cost-balanced set of heads instead
+            # of the contiguous chunk; only slot numbers inside the exchange change
+            if balance.enabled():
+                head_at = balance.balance_heads(list(branch), balance.branch_costs(plan), SP_STATE.sp_size)
+            branch = local_heads(list(branch), heads, head_at)
         if weights is not None:
             weights = weights[:, r * hp:(r + 1) * hp]
+        mine = list(head_at[r * hp:(r + 1) * hp]) if head_at is not None else list(range(r * hp, (r + 1) * hp))
         ex = get_exchange(heads, query.shape[2], query.device) if (weights is None and query.shape[0] == 1) else None
         if ex is not None:
             # NVLink peer-memory path: Q/K/V rows are stored straight into the owner ranks' buffers, and the attention
             # epilogue stores every output row straight into the buffer of the rank that owns the token
-            q, k, v = ex.scatter_qkv(query, key, value)
+            q, k, v = ex.scatter_qkv(query, key, value, head_at)
             ops.routed_attention(plan, q, k, v, branch=branch, out_peers=ex.out_ptrs, out_peer_rows=ex.s_loc,
-                                 out_peer_strides=(0, 128, heads * 128), head_offset=r * hp)
+                                 out_peer_strides=(0, 128, heads * 128), out_heads=mine)
             return ex.finish_out()
-        query, key, value = exchange_qkv(query, key, value)
+        query, key, value = exchange_qkv(query, key, value, head_at=head_at)
         out = ops.routed_attention(plan, query, key, value, branch=branch, weights=weights)
-        return exchange_out(out)
+        return exchange_out(out, head_at)
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, rotary_emb: Optional[torch.Tensor] = None,

@@ -38,10 +38,11 @@ int launch_router(const void* temb, int temb_dtype, const void* w, const void* b
                   int64_t w_layer_stride, int64_t bias_layer_stride, int n_layers, int batch, int embed_dim,
                   int heads, float tau, float* scores, int32_t* branch, cudaStream_t stream);
 int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
-                           int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream);
+                           int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, const int32_t* head_at,
+                           cudaStream_t stream);
 int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                             const int64_t* stride_h, void* send, int s_loc, int heads, int world,
-                            cudaStream_t stream);
+                            const int32_t* head_at, cudaStream_t stream);
 int launch_ln_modulate(const void* x, const float* w, const float* b, const float* scale, const float* shift, void* out,
                        int64_t rows, int dim, int rows_per_batch, float eps, cudaStream_t stream);
 int launch_gate_residual(const void* x, const void* y, const float* gate, void* out, int64_t rows, int dim,
@@ -50,7 +51,7 @@ int launch_rmsnorm_rope(const void* x, const void* weight, const float* cs, cons
                         int dim, int tokens_per_batch, float eps, cudaStream_t stream);
 int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                                const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int heads,
-                               int world, int rank, cudaStream_t stream);
+                               int world, int rank, const int32_t* head_at, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
@@ -600,7 +601,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     std::vector<AttnHead> v(hs.size());
     for (size_t i = 0; i < hs.size(); ++i) {
       v[i].hk = slot_is_index ? static_cast<int32_t>(i) : hs[i];
-      v[i].ho = hs[i];
+      v[i].ho = a.out_heads ? a.out_heads[hs[i]] : hs[i];
       v[i].weight = blend ? a.weights[(static_cast<int64_t>(b) * a.heads + hs[i]) * 3 + e] : 1.f;
       v[i].flags = (blend && e > 0) ? 1 : 0;
     }
@@ -850,34 +851,37 @@ int64_t vb_stats_launches(void) { return g_launches; }
 double vb_stats_attn_flops(void) { return g_flops; }
 
 int vb_ulysses_pack_heads(const void* x, void* send, int32_t s_loc, int32_t heads, int32_t world, int32_t n_tensors,
-                          int64_t x_tensor_stride, int64_t send_tensor_stride, vb_stream_t stream) {
+                          int64_t x_tensor_stride, int64_t send_tensor_stride, const int32_t* head_at,
+                          vb_stream_t stream) {
   VB_REQUIRE(x && send, VB_ERR_INVALID, "null argument");
   int rc = launch_ulysses_permute(x, send, s_loc, heads, world, n_tensors, x_tensor_stride, send_tensor_stride, 1,
-                                  static_cast<cudaStream_t>(stream));
+                                  head_at, static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }
 int vb_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s, const int64_t* stride_h,
-                        void* send, int32_t s_loc, int32_t heads, int32_t world, vb_stream_t stream) {
+                        void* send, int32_t s_loc, int32_t heads, int32_t world, const int32_t* head_at,
+                        vb_stream_t stream) {
   VB_REQUIRE(q && k && v && send && stride_s && stride_h, VB_ERR_INVALID, "null argument");
-  int rc = launch_ulysses_pack_qkv(q, k, v, stride_s, stride_h, send, s_loc, heads, world,
+  int rc = launch_ulysses_pack_qkv(q, k, v, stride_s, stride_h, send, s_loc, heads, world, head_at,
                                    static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }
 int vb_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                            const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
-                           int32_t heads, int32_t world, int32_t rank, vb_stream_t stream) {
+                           int32_t heads, int32_t world, int32_t rank, const int32_t* head_at, vb_stream_t stream) {
   VB_REQUIRE(q && k && v && stride_s && stride_h && peer_qkv, VB_ERR_INVALID, "null argument");
   int rc = launch_ulysses_scatter_qkv(q, k, v, stride_s, stride_h, peer_qkv, rows_total, s_loc, heads, world, rank,
-                                      static_cast<cudaStream_t>(stream));
+                                      head_at, static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }
 int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
-                            vb_stream_t stream) {
+                            const int32_t* head_at, vb_stream_t stream) {
   VB_REQUIRE(recv && y, VB_ERR_INVALID, "null argument");
-  int rc = launch_ulysses_permute(recv, y, s_loc, heads, world, 1, 0, 0, 0, static_cast<cudaStream_t>(stream));
+  int rc = launch_ulysses_permute(recv, y, s_loc, heads, world, 1, 0, 0, 0, head_at,
+                                  static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }

@@ -36,6 +36,7 @@ constexpr int kHeadDim = 128;     // D of every supported model (Wan 1.3B/14B, H
 constexpr int kBlockM = 128;      // query rows per MMA tile (one TMEM lane per row)
 constexpr int kBlockN = 128;      // keys per MMA tile
 constexpr int kMaxHeads = 64;     // heads per attention launch
+constexpr int kMaxHeadTable = 128; // heads per Ulysses exchange (slot -> head table passed by value)
 
 // One CTA's work: up to two 128-row query tiles that share the same key/value run list.
 struct QPair {

@@ -323,10 +323,30 @@ int launch_router(const void* temb, int temb_dtype, const void* w, const void* b
 //   pack  : x (S_loc, H, 128) -> send (P, S_loc, H/P, 128)
 //   unpack: recv (P, S_loc, H/P, 128) -> y (S_loc, H, 128)
 // Both are a permutation of 256-byte head rows; one half-warp per row, 16-byte vectors.
+// Slot (p, i) of the exchanged layout holds head `at[p * H/P + i]`: the identity for the reference's contiguous head
+// chunks, or the cost-balanced assignment the host derives from the step's routing.
 // ------------------------------------------------------------------------------------------------
+struct HeadTable {
+  uint8_t at[kMaxHeadTable];
+};
+
+static int fill_head_table(HeadTable& t, const int32_t* head_at, int heads) {
+  VB_REQUIRE(heads <= kMaxHeadTable, VB_ERR_UNSUPPORTED, "at most %d heads per exchange, got %d", kMaxHeadTable, heads);
+  uint8_t seen[kMaxHeadTable] = {0};
+  for (int i = 0; i < heads; ++i) {
+    const int h = head_at ? head_at[i] : i;
+    VB_REQUIRE(h >= 0 && h < heads && !seen[h], VB_ERR_INVALID, "head_at is not a permutation of [0, %d) at slot %d",
+               heads, i);
+    seen[h] = 1;
+    t.at[i] = static_cast<uint8_t>(h);
+  }
+  return VB_OK;
+}
+
 __global__ void __launch_bounds__(256)
-vb_ulysses_permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int s_loc, int heads, int world,
-                          int n_tensors, int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack) {
+vb_ulysses_permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const HeadTable tab, int s_loc,
+                          int heads, int world, int n_tensors, int64_t src_tensor_stride, int64_t dst_tensor_stride,
+                          int pack) {
   const int hp = heads / world;
   const int64_t rows = static_cast<int64_t>(s_loc) * heads;
   const int64_t total = rows * n_tensors * 16;
@@ -336,11 +356,12 @@ vb_ulysses_permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst
     int64_t r = i >> 4;
     const int t = static_cast<int>(r / rows);
     r %= rows;
-    // r indexes the token-major side: (s, h)
-    const int h = static_cast<int>(r % heads);
+    // r indexes (token, slot); the head in that slot comes from the table
+    const int slot = static_cast<int>(r % heads);
     const int64_t s = r / heads;
-    const int64_t tm = (s * heads + h) * 16 + c;                                   // (S_loc, H, 128)
-    const int64_t pm = ((static_cast<int64_t>(h / hp) * s_loc + s) * hp + (h % hp)) * 16 + c;  // (P, S_loc, H/P, 128)
+    const int h = tab.at[slot];
+    const int64_t tm = (s * heads + h) * 16 + c;                                         // (S_loc, H, 128)
+    const int64_t pm = ((static_cast<int64_t>(slot / hp) * s_loc + s) * hp + (slot % hp)) * 16 + c;  // (P, S_loc, H/P, 128)
     if (pack) dst[t * (dst_tensor_stride >> 3) + pm] = src[t * (src_tensor_stride >> 3) + tm];
     else dst[t * (dst_tensor_stride >> 3) + tm] = src[t * (src_tensor_stride >> 3) + pm];
   }
@@ -354,7 +375,8 @@ struct PackQkvParams {
 };
 
 __global__ void __launch_bounds__(256)
-vb_ulysses_pack_qkv_kernel(const PackQkvParams p, uint4* __restrict__ send, int s_loc, int heads, int world) {
+vb_ulysses_pack_qkv_kernel(const PackQkvParams p, const HeadTable tab, uint4* __restrict__ send, int s_loc, int heads,
+                           int world) {
   const int hp = heads / world;
   const int64_t rows = static_cast<int64_t>(s_loc) * heads;
   const int64_t total = rows * 3 * 16;
@@ -364,16 +386,17 @@ vb_ulysses_pack_qkv_kernel(const PackQkvParams p, uint4* __restrict__ send, int 
     int64_t r = i >> 4;
     const int t = static_cast<int>(r / rows);
     r %= rows;
-    const int h = static_cast<int>(r % heads);
+    const int slot = static_cast<int>(r % heads);
     const int64_t s = r / heads;
-    const int64_t dst = ((((static_cast<int64_t>(t) * world + h / hp) * s_loc + s) * hp) + (h % hp)) * 16 + c;
+    const int h = tab.at[slot];
+    const int64_t dst = ((((static_cast<int64_t>(t) * world + slot / hp) * s_loc + s) * hp) + (slot % hp)) * 16 + c;
     send[dst] = p.src[t][(s * p.stride_s[t] + h * p.stride_h[t]) / 8 + c];
   }
 }
 
 int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                             const int64_t* stride_h, void* send, int s_loc, int heads, int world,
-                            cudaStream_t stream) {
+                            const int32_t* head_at, cudaStream_t stream) {
   VB_REQUIRE(world > 0 && heads % world == 0, VB_ERR_INVALID, "heads %d not divisible by world %d", heads, world);
   PackQkvParams p;
   p.src[0] = static_cast<const uint4*>(q);
@@ -385,10 +408,12 @@ int launch_ulysses_pack_qkv(const void* q, const void* k, const void* v, const i
     p.stride_s[i] = stride_s[i];
     p.stride_h[i] = stride_h[i];
   }
+  HeadTable tab;
+  if (int rc = fill_head_table(tab, head_at, heads)) return rc;
   const int64_t total = static_cast<int64_t>(s_loc) * heads * 3 * 16;
   if (total == 0) return VB_OK;
   const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  vb_ulysses_pack_qkv_kernel<<<grid, 256, 0, stream>>>(p, static_cast<uint4*>(send), s_loc, heads, world);
+  vb_ulysses_pack_qkv_kernel<<<grid, 256, 0, stream>>>(p, tab, static_cast<uint4*>(send), s_loc, heads, world);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }
@@ -401,7 +426,8 @@ struct ScatterQkvParams {
 // Stores every (token, head) row of q, k, v into the receive buffer of the rank that owns the head: the Ulysses "in"
 // exchange as plain NVLink stores (16-byte vectors, 256-byte rows), no staging copy and no collective call.
 __global__ void __launch_bounds__(256)
-vb_ulysses_scatter_qkv_kernel(const ScatterQkvParams p, int64_t rows_total, int s_loc, int heads, int world, int rank) {
+vb_ulysses_scatter_qkv_kernel(const ScatterQkvParams p, const HeadTable tab, int64_t rows_total, int s_loc, int heads,
+                              int world, int rank) {
   const int hp = heads / world;
   const int64_t rows = static_cast<int64_t>(s_loc) * heads;
   const int64_t total = rows * 3 * 16;
@@ -416,7 +442,7 @@ vb_ulysses_scatter_qkv_kernel(const ScatterQkvParams p, int64_t rows_total, int 
     r /= s_loc;
     const int peer = static_cast<int>(r % world);
     const int t = static_cast<int>(r / world);
-    const int hsrc = peer * hp + hh;
+    const int hsrc = tab.at[peer * hp + hh];
     const uint4 val = p.src[t][(sidx * p.stride_s[t] + hsrc * p.stride_h[t]) / 8 + c];
     const int64_t dst = ((static_cast<int64_t>(t) * rows_total + static_cast<int64_t>(rank) * s_loc + sidx) * hp + hh) * 16 + c;
     p.peer[peer][dst] = val;
@@ -425,7 +451,7 @@ vb_ulysses_scatter_qkv_kernel(const ScatterQkvParams p, int64_t rows_total, int 
 
 int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                                const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int heads,
-                               int world, int rank, cudaStream_t stream) {
+                               int world, int rank, const int32_t* head_at, cudaStream_t stream) {
   VB_REQUIRE(world > 0 && world <= 8 && heads % world == 0, VB_ERR_INVALID, "heads %d / world %d not supported", heads,
              world);
   ScatterQkvParams p;
@@ -438,23 +464,28 @@ int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, cons
     p.stride_h[i] = stride_h[i];
   }
   for (int i = 0; i < 8; ++i) p.peer[i] = i < world ? static_cast<uint4*>(peer_qkv[i]) : nullptr;
+  HeadTable tab;
+  if (int rc = fill_head_table(tab, head_at, heads)) return rc;
   const int64_t total = static_cast<int64_t>(s_loc) * heads * 3 * 16;
   if (total == 0) return VB_OK;
   const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  vb_ulysses_scatter_qkv_kernel<<<grid, 256, 0, stream>>>(p, rows_total, s_loc, heads, world, rank);
+  vb_ulysses_scatter_qkv_kernel<<<grid, 256, 0, stream>>>(p, tab, rows_total, s_loc, heads, world, rank);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }
 
 int launch_ulysses_permute(const void* src, void* dst, int s_loc, int heads, int world, int n_tensors,
-                           int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, cudaStream_t stream) {
+                           int64_t src_tensor_stride, int64_t dst_tensor_stride, int pack, const int32_t* head_at,
+                           cudaStream_t stream) {
   VB_REQUIRE(world > 0 && heads % world == 0, VB_ERR_INVALID, "heads %d not divisible by world %d", heads, world);
   VB_REQUIRE(src_tensor_stride % 8 == 0 && dst_tensor_stride % 8 == 0, VB_ERR_INVALID,
              "tensor strides must be multiples of 8 elements");
+  HeadTable tab;
+  if (int rc = fill_head_table(tab, head_at, heads)) return rc;
   const int64_t total = static_cast<int64_t>(s_loc) * heads * n_tensors * 16;
   if (total == 0) return VB_OK;
   const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  vb_ulysses_permute_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst),
+  vb_ulysses_permute_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), tab,
                                                       s_loc, heads, world, n_tensors, src_tensor_stride,
                                                       dst_tensor_stride, pack);
   VB_CUDA_OK(cudaGetLastError());

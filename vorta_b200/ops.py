@@ -127,11 +127,12 @@ def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
                      flags: int = 0, out: Optional[torch.Tensor] = None,
                      debug: Optional[torch.Tensor] = None, out_peers: Optional[Sequence[int]] = None,
                      out_peer_rows: int = 0, out_peer_strides: Optional[Sequence[int]] = None,
-                     head_offset: int = 0) -> Optional[torch.Tensor]:
+                     head_offset: int = 0, out_heads: Optional[Sequence[int]] = None) -> Optional[torch.Tensor]:
     """One routed self-attention layer.  q, k, v: (B, H, S + text_len, 128) bf16 views (any batch / head / token
     strides).  ``branch``: per-head VB_BRANCH_* ids (Eval processor semantics, wan.py:388-438); ``weights``:
     (B, H, 3) routing scores for the blended Train semantics (wan.py:296-300).  Returns (B, H, N, 128) as a view
-    of (B, N, H, 128) memory, so ``transpose(1, 2).flatten(2, 3)`` (wan.py:152) is free."""
+    of (B, N, H, 128) memory, so ``transpose(1, 2).flatten(2, 3)`` (wan.py:152) is free.
+    ``out_heads``: head index along the output's head stride for each local head (default: ``head_offset + h``)."""
     for name, t in (("q", q), ("k", k), ("v", v)):
         _require_cuda_bf16(name, t)
     B, H, N, D = q.shape
@@ -140,14 +141,16 @@ def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
                          f" (+ text {plan.text_len}).")
     args = L.AttnArgs()
     if out_peers is not None:
-        # fused Ulysses "out" exchange: rows go straight into the owner ranks' (S_loc, H_total, 128) buffers; this
-        # rank's heads start at head_offset there (folded into the base pointers)
+        # fused Ulysses "out" exchange: rows go straight into the owner ranks' (S_loc, H_total, 128) buffers; local
+        # head h lands at head out_heads[h] there
         out = None
         sb, sh, ss = out_peer_strides
         args.out = None
         args.out_stride[:] = (sb, sh, ss)
         for i, ptr in enumerate(out_peers):
-            args.out_peer_ptrs[i] = int(ptr) + head_offset * sh * 2
+            args.out_peer_ptrs[i] = int(ptr)
+        if out_heads is None:
+            out_heads = range(head_offset, head_offset + H)
         args.out_peer_count, args.out_peer_rows = len(out_peers), int(out_peer_rows)
     else:
         if out is None:
@@ -176,6 +179,12 @@ def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
         args.branch = C.cast(br, C.POINTER(C.c_int32))
     else:
         args.branch = None
+    if out_heads is not None:
+        oh = (C.c_int32 * H)(*[int(x) for x in out_heads])
+        keep.append(oh)
+        args.out_heads = C.cast(oh, C.POINTER(C.c_int32))
+    else:
+        args.out_heads = None
     args.flags = int(flags)
     ws = plan.workspace(B, H, q.device)
     args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -52,16 +52,18 @@ class PeerExchange:
         self.qkv_ptrs = (C.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])
         self.out_ptrs = [int(p) for p in self.h_out.buffer_ptrs]
 
-    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor
+    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head_at: Optional[Sequence[int]] = None
                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  Returns (1, H/P, S, 128) views of the local
-        receive buffer, valid after barrier A (issued here)."""
+        receive buffer, valid after barrier A (issued here).  ``head_at``: slot -> head table of a balanced placement
+        (``balance.balance_heads``), None = contiguous head chunks."""
         i64x3 = C.c_int64 * 3
+        table = (C.c_int32 * self.heads)(*[int(h) for h in head_at]) if head_at is not None else None
         with torch.cuda.device(q.device):
             L.check(L.lib().vb_ulysses_scatter_qkv(
                 q.data_ptr(), k.data_ptr(), v.data_ptr(), i64x3(q.stride(2), k.stride(2), v.stride(2)),
                 i64x3(q.stride(1), k.stride(1), v.stride(1)), self.qkv_ptrs, self.S, self.s_loc, self.heads, self.P,
-                self.rank, torch.cuda.current_stream(q.device).cuda_stream))
+                self.rank, table, torch.cuda.current_stream(q.device).cuda_stream))
         self.h_qkv.barrier(channel=0)
         return tuple(self.qkv[i].unsqueeze(0).transpose(1, 2) for i in range(3))
 

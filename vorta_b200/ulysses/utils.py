@@ -12,7 +12,7 @@ directly in send order, so a layer costs two collectives and two layout passes i
 from __future__ import annotations
 
 import ctypes as C
-from typing import Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -30,32 +30,43 @@ def _a2a(recv: torch.Tensor, send: torch.Tensor) -> None:
     dist.all_to_all_single(recv, send, group=SP_STATE.group)
 
 
-def pack_heads(x: torch.Tensor, world: int) -> torch.Tensor:
+def _head_table(head_at: Optional[Sequence[int]], heads: int):
+    """ctypes int32[H] of a slot -> head table (None = the reference's contiguous chunks)."""
+    if head_at is None:
+        return None
+    if len(head_at) != heads:
+        raise ValueError(f"head_at has {len(head_at)} entries for {heads} heads")
+    return (C.c_int32 * heads)(*[int(h) for h in head_at])
+
+
+def pack_heads(x: torch.Tensor, world: int, head_at: Optional[Sequence[int]] = None) -> torch.Tensor:
     """x: (n_tensors, S_loc, H, 128) bf16 contiguous -> (n_tensors, P, S_loc, H/P, 128)."""
     n, s_loc, H, D = x.shape
     send = torch.empty((n, world, s_loc, H // world, D), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
         L.check(L.lib().vb_ulysses_pack_heads(x.data_ptr(), send.data_ptr(), s_loc, H, world, n, x.stride(0),
-                                              send.stride(0), _stream(x.device)))
+                                              send.stride(0), _head_table(head_at, H), _stream(x.device)))
     return send
 
 
-def unpack_heads(recv: torch.Tensor) -> torch.Tensor:
+def unpack_heads(recv: torch.Tensor, head_at: Optional[Sequence[int]] = None) -> torch.Tensor:
     """recv: (P, S_loc, H/P, 128) -> (S_loc, H, 128)."""
     world, s_loc, hp, D = recv.shape
     y = torch.empty((s_loc, hp * world, D), dtype=recv.dtype, device=recv.device)
     with torch.cuda.device(recv.device):
         L.check(L.lib().vb_ulysses_unpack_heads(recv.data_ptr(), y.data_ptr(), s_loc, hp * world, world,
-                                                _stream(recv.device)))
+                                                _head_table(head_at, hp * world), _stream(recv.device)))
     return y
 
 
-def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: int = 0
-                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: int = 0,
+                 head_at: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """q, k, v: (1, H, S_loc, 128) views: this rank's token shard, all heads.
     Each tensor may have its own (token, head) strides.
     Returns (1, H/P, S + extra_rows, 128) views of token-major memory: this rank's head chunk over the full
-    sequence; ``extra_rows`` uninitialised rows are left at the end for the caller (HunyuanVideo text tokens)."""
+    sequence; ``extra_rows`` uninitialised rows are left at the end for the caller (HunyuanVideo text tokens).
+    ``head_at``: slot -> head table of a balanced placement (``balance.balance_heads``); rank r then holds heads
+    ``head_at[r*H/P:(r+1)*H/P]`` instead of the contiguous chunk."""
     P = SP_STATE.sp_size
     B, H, s_loc, D = q.shape
     if B != 1:
@@ -72,7 +83,8 @@ def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: 
         L.check(L.lib().vb_ulysses_pack_qkv(q.data_ptr(), k.data_ptr(), v.data_ptr(),
                                             i64x3(q.stride(2), k.stride(2), v.stride(2)),
                                             i64x3(q.stride(1), k.stride(1), v.stride(1)),
-                                            send.data_ptr(), s_loc, H, P, _stream(q.device)))
+                                            send.data_ptr(), s_loc, H, P, _head_table(head_at, H),
+                                            _stream(q.device)))
     out = []
     for i in range(3):
         # chunk p of the receive buffer = tokens of rank p for my head chunk: (S, hp, D) token-major, in place
@@ -82,8 +94,9 @@ def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: 
     return tuple(out)
 
 
-def exchange_out(o: torch.Tensor) -> torch.Tensor:
-    """o: (1, H/P, S, 128) view of (1, S, H/P, 128) memory -> (1, H, S_loc, 128) view of (1, S_loc, H, 128)."""
+def exchange_out(o: torch.Tensor, head_at: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """o: (1, H/P, S, 128) view of (1, S, H/P, 128) memory -> (1, H, S_loc, 128) view of (1, S_loc, H, 128).
+    ``head_at`` must be the table the matching ``exchange_qkv`` used; heads come back in their original order."""
     P = SP_STATE.sp_size
     B, hp, S, D = o.shape
     s_loc = S // P
@@ -92,7 +105,7 @@ def exchange_out(o: torch.Tensor) -> torch.Tensor:
         send = send.contiguous()
     recv = torch.empty_like(send)
     _a2a(recv, send)
-    y = unpack_heads(recv)                                            # (S_loc, H, D)
+    y = unpack_heads(recv, head_at)                                   # (S_loc, H, D)
     return y.unsqueeze(0).transpose(1, 2)
 
 
@@ -132,10 +145,12 @@ def shrink_dim(tensor: torch.Tensor, dim: int) -> torch.Tensor:
     return tensor
 
 
-def local_heads(values, heads: int):
-    """Slice a per-head list (branch ids, weights rows) down to this rank's head chunk."""
+def local_heads(values, heads: int, head_at: Optional[Sequence[int]] = None):
+    """Slice a per-head list (branch ids, weights rows) down to the heads this rank holds."""
     if not SP_STATE.enabled:
         return values
     hp = heads // SP_STATE.sp_size
     r = SP_STATE.group_local_rank
+    if head_at is not None:
+        return [values[h] for h in head_at[r * hp:(r + 1) * hp]]
     return values[r * hp:(r + 1) * hp]
