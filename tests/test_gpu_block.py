@@ -17,7 +17,7 @@ def _close(out, ref, atol=None):
     assert float((out.float() - ref16).abs().max()) <= float(tol.max())
 
 
-@pytest.mark.parametrize("B,S,dim", [(1, 333, 1536), (2, 130, 5120), (1, 64, 384)])
+@pytest.mark.parametrize("B,S,dim", [(1, 333, 1536), (2, 130, 5120), (1, 64, 384), (1, 71, 3072), (2, 9, 2048)])
 def test_ln_modulate(B, S, dim):
     g = torch.Generator().manual_seed(dim)
     x = (torch.randn((B, S, dim), generator=g) * 2 + 0.3).to(torch.bfloat16).cuda()
@@ -42,7 +42,7 @@ def test_gate_residual(B, S, dim):
     _close(ops.gate_residual(x, y, None), x.float() + y.float())
 
 
-@pytest.mark.parametrize("B,S,heads", [(1, 200, 12), (2, 77, 40), (1, 96, 3)])
+@pytest.mark.parametrize("B,S,heads", [(1, 200, 12), (2, 77, 40), (1, 96, 3), (1, 53, 24), (1, 5, 16)])
 def test_rmsnorm_rope(B, S, heads):
     dim = heads * 128
     g = torch.Generator().manual_seed(heads)

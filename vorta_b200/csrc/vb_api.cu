@@ -54,8 +54,8 @@ int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, cons
                                int world, int rank, const int32_t* head_at, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
-int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
-                int n_pairs, int n_heads, int batch, cudaStream_t stream);
+int launch_attn(const AttnTmaps& tmaps, const AttnParams& params, int n_ctas, cudaStream_t stream);
+
 
 // ---- schedule tables ----------------------------------------------------------------------------
 struct Schedule {
@@ -508,57 +508,97 @@ struct BranchLaunch {
 };
 }  // namespace
 
-// Launch one branch for the head slots in `heads` (<= kMaxHeads per launch).
+// One branch with the head slots it covers.
+struct Segment {
+  BranchLaunch bl;
+  std::vector<AttnHead> heads;
+};
+
+// Launch up to kMaxSegments branches as ONE grid (segments in the given order = longest CTAs first), covering
+// batches [batch0, batch0 + nbatch).  The caller guarantees that the segments write disjoint outputs or that a single
+// segment is passed (blend mode accumulates branch after branch and therefore launches them one by one).
+static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_args& a, int batch0, int nbatch,
+                           cudaStream_t stream) {
+  AttnTmaps tm;
+  AttnParams p;
+  memset(&tm, 0, sizeof(tm));
+  memset(&p, 0, sizeof(p));
+  int rc, n_used = 0, head0 = 0;
+  int64_t n_ctas = 0;
+  double flops = 0.0;
+  for (int i = 0; i < n_seg; ++i) {
+    const Segment& sg = *segs[i];
+    const BranchLaunch& bl = sg.bl;
+    if (sg.heads.empty() || bl.sched->pairs.empty()) continue;
+    VB_REQUIRE(head0 + sg.heads.size() <= static_cast<size_t>(kMaxHeads), VB_ERR_INVALID,
+               "more than %d heads in one attention launch", kMaxHeads);
+    CUtensorMap* m = tm.m[n_used];
+    if ((rc = make_qkv_tensor_map(&m[0], bl.q, bl.n_rows_q, bl.n_heads_tensor, a.batch, bl.qs[0], bl.qs[1], bl.qs[2])))
+      return rc;
+    if ((rc = make_qkv_tensor_map(&m[1], bl.k, bl.n_rows_kv, bl.n_heads_tensor, a.batch, bl.ks[0], bl.ks[1], bl.ks[2])))
+      return rc;
+    if ((rc = make_qkv_tensor_map(&m[2], bl.v, bl.n_rows_kv, bl.n_heads_tensor, a.batch, bl.vs[0], bl.vs[1], bl.vs[2])))
+      return rc;
+    AttnSeg& s = p.seg[n_used];
+    s.pairs = bl.sched->d_pairs;
+    s.runs = bl.sched->d_runs;
+    s.out_map = bl.out_map; s.out_map_stride_b = bl.out_map_stride_b; s.out_map_stride_h = bl.out_map_stride_h;
+    s.bcast_map = bl.bcast_map; s.bcast_stride_b = bl.bcast_stride_b; s.bcast_stride_h = bl.bcast_stride_h;
+    s.bcast_rows = bl.bcast_rows; s.bcast_n = bl.bcast_n;
+    s.n_pairs = static_cast<int32_t>(bl.sched->pairs.size());
+    s.n_heads = static_cast<int32_t>(sg.heads.size());
+    s.head0 = head0;
+    s.cta_begin = static_cast<int32_t>(n_ctas);
+    for (size_t h = 0; h < sg.heads.size(); ++h) p.heads[head0 + h] = sg.heads[h];
+    head0 += s.n_heads;
+    n_ctas += static_cast<int64_t>(s.n_pairs) * s.n_heads * nbatch;
+    flops += bl.sched->flops_per_head * s.n_heads * nbatch;
+    ++n_used;
+  }
+  if (n_used == 0) return VB_OK;
+  VB_REQUIRE(n_ctas < (1ll << 31), VB_ERR_UNSUPPORTED, "attention grid too large");
+  p.n_seg = n_used;
+  p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.out_stride_b = a.out_stride[0]; p.out_stride_h = a.out_stride[1]; p.out_stride_s = a.out_stride[2];
+  p.out_peer_count = a.out_peer_count;
+  p.out_peer_rows = a.out_peer_rows;
+  for (int i = 0; i < 8; ++i)
+    p.out_peers[i] = i < a.out_peer_count ? static_cast<__nv_bfloat16*>(a.out_peer_ptrs[i]) : nullptr;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+  p.batch0 = batch0;
+  p.dbg = a.debug;
+  if (a.debug != nullptr) {   // bring-up only: descriptor stride overrides for the V operand
+    if (const char* e = getenv("VB_DBG_V_LBO")) p.dbg_v_lbo = static_cast<uint32_t>(atoi(e));
+    if (const char* e = getenv("VB_DBG_V_SBO")) p.dbg_v_sbo = static_cast<uint32_t>(atoi(e));
+  }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_timing) {
+    VB_CUDA_OK(cudaEventCreate(&ev0));
+    VB_CUDA_OK(cudaEventCreate(&ev1));
+    VB_CUDA_OK(cudaEventRecord(ev0, stream));
+  }
+  rc = launch_attn(tm, p, static_cast<int>(n_ctas), stream);
+  if (rc != VB_OK) return rc;
+  if (g_timing) {
+    VB_CUDA_OK(cudaEventRecord(ev1, stream));
+    g_events.push_back({ev0, ev1});
+    g_timed_flops += flops;
+  }
+  ++g_launches;
+  g_flops += flops;
+  return VB_OK;
+}
+
+// Launch one branch for the head slots in `heads`, in chunks of <= kMaxHeads.
 static int run_branch(const BranchLaunch& bl, const vb_attn_args& a, const std::vector<AttnHead>& heads, int batch0,
                       int nbatch, cudaStream_t stream) {
-  if (heads.empty() || bl.sched->pairs.empty()) return VB_OK;
-  CUtensorMap mq, mk, mv;
-  int rc;
-  if ((rc = make_qkv_tensor_map(&mq, bl.q, bl.n_rows_q, bl.n_heads_tensor, a.batch, bl.qs[0], bl.qs[1], bl.qs[2])))
-    return rc;
-  if ((rc = make_qkv_tensor_map(&mk, bl.k, bl.n_rows_kv, bl.n_heads_tensor, a.batch, bl.ks[0], bl.ks[1], bl.ks[2])))
-    return rc;
-  if ((rc = make_qkv_tensor_map(&mv, bl.v, bl.n_rows_kv, bl.n_heads_tensor, a.batch, bl.vs[0], bl.vs[1], bl.vs[2])))
-    return rc;
   for (size_t h0 = 0; h0 < heads.size(); h0 += kMaxHeads) {
-    AttnParams p;
-    memset(&p, 0, sizeof(p));
-    p.pairs = bl.sched->d_pairs;
-    p.runs = bl.sched->d_runs;
-    p.out = static_cast<__nv_bfloat16*>(a.out);
-    p.out_stride_b = a.out_stride[0]; p.out_stride_h = a.out_stride[1]; p.out_stride_s = a.out_stride[2];
-    p.out_map = bl.out_map; p.out_map_stride_b = bl.out_map_stride_b; p.out_map_stride_h = bl.out_map_stride_h;
-    p.bcast_map = bl.bcast_map; p.bcast_stride_b = bl.bcast_stride_b; p.bcast_stride_h = bl.bcast_stride_h;
-    p.bcast_rows = bl.bcast_rows; p.bcast_n = bl.bcast_n;
-    p.out_peer_count = a.out_peer_count;
-    p.out_peer_rows = a.out_peer_rows;
-    for (int i = 0; i < 8; ++i)
-      p.out_peers[i] = i < a.out_peer_count ? static_cast<__nv_bfloat16*>(a.out_peer_ptrs[i]) : nullptr;
-    p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
-    p.batch0 = batch0;
-    p.dbg = a.debug;
-    if (a.debug != nullptr) {   // bring-up only: descriptor stride overrides for the V operand
-      if (const char* e = getenv("VB_DBG_V_LBO")) p.dbg_v_lbo = static_cast<uint32_t>(atoi(e));
-      if (const char* e = getenv("VB_DBG_V_SBO")) p.dbg_v_sbo = static_cast<uint32_t>(atoi(e));
-    }
-    const int n = static_cast<int>(std::min<size_t>(kMaxHeads, heads.size() - h0));
-    p.n_heads = n;
-    for (int i = 0; i < n; ++i) p.heads[i] = heads[h0 + i];
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (g_timing) {
-      VB_CUDA_OK(cudaEventCreate(&ev0));
-      VB_CUDA_OK(cudaEventCreate(&ev1));
-      VB_CUDA_OK(cudaEventRecord(ev0, stream));
-    }
-    rc = launch_attn(mq, mk, mv, p, static_cast<int>(bl.sched->pairs.size()), n, nbatch, stream);
+    Segment sg;
+    sg.bl = bl;
+    sg.heads.assign(heads.begin() + h0, heads.begin() + std::min(heads.size(), h0 + static_cast<size_t>(kMaxHeads)));
+    const Segment* one = &sg;
+    int rc = launch_segments(&one, 1, a, batch0, nbatch, stream);
     if (rc != VB_OK) return rc;
-    if (g_timing) {
-      VB_CUDA_OK(cudaEventRecord(ev1, stream));
-      g_events.push_back({ev0, ev1});
-      g_timed_flops += bl.sched->flops_per_head * n * nbatch;
-    }
-    ++g_launches;
-    g_flops += bl.sched->flops_per_head * n * nbatch;
   }
   return VB_OK;
 }
@@ -614,7 +654,19 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     return VB_OK;
   };
   // blend weights differ per batch element; top-1 routing is shared by the batch (wan.py:398)
+  // top-1 mode: every head is in exactly one branch, so the branches write disjoint outputs and run as segments of ONE
+  // launch after all selection / gather passes have been issued; kept in branch order full, coreset, sliding, which is
+  // longest-CTA-first (full: S/128 key blocks per CTA, coreset: ~S/256, sliding: <= 27 tiles)
+  Segment deferred[kMaxSegments];
+  int n_deferred = 0;
+  const bool merge = !blend && a.heads <= kMaxHeads && getenv("VB_ATTN_SPLIT_LAUNCHES") == nullptr;
   auto for_batches = [&](const BranchLaunch& bl, const std::vector<int32_t>& hs, int e, bool slot_is_index) -> int {
+    if (merge) {
+      deferred[n_deferred].bl = bl;
+      deferred[n_deferred].heads = head_entries(hs, e, slot_is_index, 0);
+      ++n_deferred;
+      return VB_OK;
+    }
     if (!blend) return run_branch(bl, a, head_entries(hs, e, slot_is_index, 0), 0, a.batch, stream);
     for (int b = 0; b < a.batch; ++b) {
       int r = run_branch(bl, a, head_entries(hs, e, slot_is_index, b), b, 1, stream);
@@ -747,6 +799,12 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     bl.sched = &pl->sliding;
     bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
     if ((rc = for_batches(bl, hs, 2, true)) != VB_OK) return rc;
+  }
+
+  if (n_deferred > 0) {
+    const Segment* order[kMaxSegments];
+    for (int i = 0; i < n_deferred; ++i) order[i] = &deferred[i];
+    if ((rc = launch_segments(order, n_deferred, a, 0, a.batch, stream)) != VB_OK) return rc;
   }
 
   // ---------------- padded text queries produce zeros (hunyuan.py:176; flex fully-masked rows) ----------------

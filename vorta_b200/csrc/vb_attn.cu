@@ -76,7 +76,7 @@ struct BlockWalker {
 #ifdef VB_TIMELINE               // perf experiment: clock stamps of CTA (0,0,0) -> p.dbg as int64[who][block][8]
 #define VB_STAMP(who, j, slot)                                                                         \
   do {                                                                                                 \
-    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64)         \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (j) < 64)         \
       reinterpret_cast<long long*>(p.dbg)[((who) * 64 + (j)) * 8 + (slot)] = clock64();                \
   } while (0)
 #else
@@ -96,8 +96,7 @@ __device__ __forceinline__ int count_blocks(const KvRun* runs, int n_runs) {
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constant__ AttnParams p) {
   // Everything lives in dynamic shared memory (no static __shared__), so the operand area starts at the CTA's
   // shared window base, which is 1024-byte aligned as SWIZZLE_128B needs; checked below.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -115,10 +114,19 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const QPair pair = p.pairs[blockIdx.x];
-  const AttnHead head = p.heads[blockIdx.y];
-  const int batch = blockIdx.z + p.batch0;
+  // linear CTA index -> (segment, pair, head, batch); segments are laid out longest CTAs first by the host
+  int seg_idx = 0;
+  if (p.n_seg > 1 && static_cast<int>(blockIdx.x) >= p.seg[1].cta_begin) seg_idx = 1;
+  if (p.n_seg > 2 && static_cast<int>(blockIdx.x) >= p.seg[2].cta_begin) seg_idx = 2;
+  const AttnSeg& seg = p.seg[seg_idx];
+  const int cta_local = static_cast<int>(blockIdx.x) - seg.cta_begin;
+  const QPair pair = seg.pairs[cta_local % seg.n_pairs];
+  const AttnHead head = p.heads[seg.head0 + (cta_local / seg.n_pairs) % seg.n_heads];
+  const int batch = cta_local / (seg.n_pairs * seg.n_heads) + p.batch0;
   const int nq = pair.nq;
+  const CUtensorMap& tmap_q = tmaps.m[seg_idx][0];
+  const CUtensorMap& tmap_k = tmaps.m[seg_idx][1];
+  const CUtensorMap& tmap_v = tmaps.m[seg_idx][2];
 
   if ((smem_u32(smem_raw) & 1023u) != 0) {      // SWIZZLE_128B atoms are 8 rows x 128 B
     if (threadIdx.x == 0) printf("vb_attn_fwd_kernel: dynamic shared memory base is not 1024-byte aligned\n");
@@ -128,7 +136,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* smem_kv = sm.kv;                     // kNumSlots x 32 KB
 
   const int n_runs = min(pair.run_count, 32);
-  if (threadIdx.x < n_runs) s_runs[threadIdx.x] = p.runs[pair.run_begin + threadIdx.x];
+  if (threadIdx.x < n_runs) s_runs[threadIdx.x] = seg.runs[pair.run_begin + threadIdx.x];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -310,7 +318,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tmem_ld_wait();
         if (row == 0 && h == 0) VB_STAMP(t, j, 2);
 #ifndef VB_TIMELINE
-        if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        if (p.dbg != nullptr && j == 0 && blockIdx.x == 0) {
           float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN + h * 64;   // raw scores of block 0
 #pragma unroll
           for (int c = 0; c < 2; ++c)
@@ -420,12 +428,12 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       int64_t dst_tok = 0;
       const int32_t* bc = nullptr;
       if (row_ok) {
-        dst_tok = p.out_map ? p.out_map[batch * p.out_map_stride_b + head.hk * p.out_map_stride_h + krow] : krow;
+        dst_tok = seg.out_map ? seg.out_map[batch * seg.out_map_stride_b + head.hk * seg.out_map_stride_h + krow] : krow;
         n_dst = 1;
-        if (p.bcast_map != nullptr && krow < p.bcast_rows) {
-          bc = p.bcast_map + batch * p.bcast_stride_b + head.hk * p.bcast_stride_h +
-               static_cast<int64_t>(krow) * p.bcast_n;
-          n_dst += p.bcast_n;
+        if (seg.bcast_map != nullptr && krow < seg.bcast_rows) {
+          bc = seg.bcast_map + batch * seg.bcast_stride_b + head.hk * seg.bcast_stride_h +
+               static_cast<int64_t>(krow) * seg.bcast_n;
+          n_dst += seg.bcast_n;
         }
       }
       const int64_t head_off = batch * p.out_stride_b + head.ho * p.out_stride_h + h * 64;
@@ -435,7 +443,7 @@ vb_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tmem_ld32(o_addr + c * 32, o);
         tmem_ld_wait();
 #ifndef VB_TIMELINE
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        if (p.dbg != nullptr && blockIdx.x == 0) {
           float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim + h * 64;
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(o[i]);   // un-normalised O
@@ -527,17 +535,16 @@ int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int6
   return VB_OK;
 }
 
-int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& params,
-                int n_pairs, int n_heads, int batch, cudaStream_t stream) {
+// `params.seg[i].cta_begin` must already hold the prefix sums; n_ctas = total over the segments.
+int launch_attn(const AttnTmaps& tmaps, const AttnParams& params, int n_ctas, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     VB_CUDA_OK(cudaFuncSetAttribute(vb_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmemBytes));
     configured = true;
   }
-  if (n_pairs == 0 || n_heads == 0 || batch == 0) return VB_OK;
-  dim3 grid(n_pairs, n_heads, batch);
-  vb_attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(mq, mk, mv, params);
+  if (n_ctas == 0) return VB_OK;
+  vb_attn_fwd_kernel<<<static_cast<unsigned>(n_ctas), kAttnThreads, kAttnSmemBytes, stream>>>(tmaps, params);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }

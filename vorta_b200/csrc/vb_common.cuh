@@ -59,27 +59,42 @@ struct AttnHead {
   int32_t flags;    // bit 0: accumulate into the existing output (blend of branches)
 };
 
-struct AttnParams {
+// One branch of a layer inside an attention launch: its own work table, Q/K/V tensor maps (AttnTmaps::m[i]) and row
+// maps.  A top-1 routed layer runs its (up to) three branches as three segments of ONE launch, longest CTAs first,
+// so the tail of one branch is filled by the next instead of idling the SMs between launches.
+constexpr int kMaxSegments = 3;
+struct AttnSeg {
   const QPair* pairs;
   const KvRun* runs;
-  __nv_bfloat16* out;
-  int64_t out_stride_b, out_stride_h, out_stride_s;   // elements
-  // Ulysses "peer" output: when out_peer_count > 0 token tok belongs to rank tok / out_peer_rows and its row is stored
-  // straight into that rank's buffer over NVLink (out_stride_* then describe ONE peer buffer, token index local)
-  __nv_bfloat16* out_peers[8];
-  int32_t out_peer_count, out_peer_rows;
   const int32_t* out_map;       // kernel row -> output token, nullptr = identity
   int64_t out_map_stride_h;     // per-head stride of out_map (0 = shared by all heads), indexed by hk
   int64_t out_map_stride_b;
   const int32_t* bcast_map;     // rows < bcast_rows also write bcast_n copies (coreset unpool)
   int64_t bcast_stride_h, bcast_stride_b;
   int32_t bcast_rows, bcast_n;
+  int32_t n_pairs, n_heads;     // CTAs of the segment = n_pairs * n_heads * n_batch, pair index fastest
+  int32_t head0;                // the segment's heads are AttnParams::heads[head0 .. head0 + n_heads)
+  int32_t cta_begin;            // linear CTA index of the segment's first CTA
+};
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  int64_t out_stride_b, out_stride_h, out_stride_s;   // elements
+  // Ulysses "peer" output: when out_peer_count > 0 token tok belongs to rank tok / out_peer_rows and its row is stored
+  // straight into that rank's buffer over NVLink (out_stride_* then describe ONE peer buffer, token index local)
+  __nv_bfloat16* out_peers[8];
+  int32_t out_peer_count, out_peer_rows;
   float scale_log2;             // log2(e) / sqrt(D)
-  int32_t n_heads;
-  int32_t batch0;               // batch index of blockIdx.z == 0 (blend mode launches one batch at a time)
+  int32_t n_seg;
+  int32_t batch0;               // batch index of the first batch slice (blend mode launches one batch at a time)
   float* dbg;                   // optional debug dump (bring-up only), nullptr in production
   uint32_t dbg_v_lbo, dbg_v_sbo;  // bring-up overrides of the V descriptor strides (0 = default)
+  AttnSeg seg[kMaxSegments];
   AttnHead heads[kMaxHeads];
+};
+
+struct AttnTmaps {
+  CUtensorMap m[kMaxSegments][3];   // q, k, v of each segment
 };
 
 // Coreset selection launch parameters (vb_kernels.cu)
