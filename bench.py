@@ -50,6 +50,19 @@ def measured_peaks():
     return dict(bf16=1400.0, burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)")
 
 
+def recorded_traffic(workload):
+    """DRAM bytes (read + write) per attention launch of this workload from the committed `ncu --set full` capture
+    (profiles/attn_traffic.json, written from the capture by profiles/summarize_full.py --traffic); None when no
+    capture of this workload has been committed."""
+    path = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(workload)
+        return (float(rec["dram_bytes_per_launch"]), rec["source"]) if rec else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -340,6 +353,7 @@ def run_gpu(args):
     peaks = measured_peaks()
     cfg = r["cfg"]
     achieved = r["attn_flops_step"] / (r["attn_ms_step"] * 1e-3) / 1e12 if r["attn_ms_step"] > 0 else 0.0
+    traffic, traffic_source = recorded_traffic(args.workload)
     line = dict(
         metric="dit_denoise_step_ms", value=r["ms"], unit="ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=r["ms"], higher_is_better=False, scaling="strong", vs_baseline=None, dtype="bf16",
@@ -352,7 +366,8 @@ def run_gpu(args):
         routed_attn_effective_tflops=r["job_flops"] / (r["attn_ms_max"] * 1e-3) / 1e12 if r["attn_ms_max"] > 0 else 0.0,
         attn_kernel_ms_per_step=r["attn_ms_step"],
         roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
-                      frac=achieved / peaks["bf16"], traffic=None, kernel="vb_attn_fwd_kernel",
+                      frac=achieved / peaks["bf16"], traffic=traffic, traffic_unit="bytes / launch (DRAM read + write)",
+                      traffic_source=traffic_source, kernel="vb_attn_fwd_kernel",
                       frac_of_burst=achieved / peaks["burst"], frac_of_spec_2250=achieved / 2250.0,
                       launches_per_step=r["kernel_launches_step"], peak_source=peaks["source"]),
         clocks=r["clocks"],

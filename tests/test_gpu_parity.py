@@ -93,6 +93,41 @@ def test_selection_is_a_partition_at_full_size():
     assert torch.equal(un[:, :2].cpu(), un_ref) and torch.equal(po[:, :2].cpu(), po_ref)
 
 
+def test_selection_near_ties_and_extreme_magnitudes_match_fp64_oracle():
+    """The selection kernel ranks in fp32 and falls back to fp64 when two similarities are closer than the fp32 error
+    bound or a norm leaves the range where the bound holds: near-duplicate margins (one bf16 ulp apart in one channel),
+    rows scaled by 2^-70 / 2^60 / 2^64 (fp32 squares underflow / stay finite / overflow) and all-zero rows must still
+    give the ranking of the fp64 oracle."""
+    lat, lw = (8, 6, 8), (2, 3, 2)                      # g = 12, 64 groups
+    info = O.get_group_info(lat, lw, 0.5)
+    plan = ops.Plan(lat, (1, 1, 1), (1, 1, 1), lw, 0.5)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((1, 3, plan.seq_len, 128), generator=g).to(torch.bfloat16)
+    bits = x.view(torch.int16)
+    for grp in range(info.margin_indices.shape[0]):
+        m = info.margin_indices[grp]
+        c = int(info.center_indices[grp, 0])
+        # two near-duplicate pairs per group: copy a margin, nudge one channel by one bf16 ulp
+        for a, b_, ch in ((0, 1, 5), (4, 7, 100)):
+            bits[:, :, m[b_]] = bits[:, :, m[a]]
+            bits[:, :, m[b_], ch] += 1
+        rows = torch.cat([m, torch.tensor([c])])
+        if grp % 8 == 1:
+            x[:, :, rows] = (x[:, :, rows].float() * 2.0 ** -70).to(torch.bfloat16)
+        elif grp % 8 == 2:
+            x[:, :, rows] = (x[:, :, rows].float() * 2.0 ** 60).to(torch.bfloat16)
+        elif grp % 8 == 3:
+            x[:, :, rows] = (x[:, :, rows].float() * 2.0 ** 64).to(torch.bfloat16)
+        elif grp % 8 == 4:
+            x[:, :, m[2]] = 0                            # a zero margin row: F.normalize eps path, cos = 0
+        elif grp % 8 == 5:
+            x[:, :, m[3]] = (x[:, :, m[3]].float() * 2.0 ** -70).to(torch.bfloat16)   # one tiny row among normal ones
+    assert torch.isfinite(x.float()).all()
+    un, po = ops.coreset_select(plan, x.to(dev()))
+    un_ref, po_ref = O.match(x.double(), info)
+    assert torch.equal(un.cpu(), un_ref) and torch.equal(po.cpu(), po_ref)
+
+
 def test_tile_layout_roundtrip_and_reference_order(golden):
     for rec in golden("tile_mask.pt")[:5]:
         lat, tile = rec["latent"], rec["tile"]

@@ -24,58 +24,161 @@ __device__ __forceinline__ void bf16x8_to_double(const uint4& v, double (&d)[8])
 
 // ------------------------------------------------------------------------------------------------
 // Coreset selection (reference: vorta/attention/coreset_select.py:91-113)
-//   one warp per (batch, head, group); a half-warp (16 lanes x 16 B) streams one 256-byte token row, so two
-//   margin rows are in flight per step.  <c, m>, |m|^2 and |c|^2 accumulate in fp64; the cosine similarities of
-//   the g-1 margins are ranked by counting (ascending, ties -> lower margin position first).
+//   one warp per (batch, head, group).  The ranking contract is the fp64 one: <c, m>, |m|^2 and |c|^2 accumulated in
+//   fp64, cosine similarities of the g-1 margins ranked by counting (ascending, ties -> lower margin position first).
+//   fp64 on this part costs one F2F conversion per element (16 / clk / SM) and caps the kernel at ~1/5 of HBM speed
+//   (round-1 measurement), so the similarities are first computed in fp32 — products of two bf16 values are exact
+//   in fp32, only the 127 additions round — with a rigorous error bound; the group is recomputed in fp64 only when
+//   two similarities are closer than that bound can separate (or a norm leaves the range where the bound holds).
+//   Both paths therefore produce the ranking of the fp64 computation.
+//
+//   fast path : 4 lanes per 256-byte token row (64 B per lane), 8 rows per warp step, every row of the group
+//               requested before the first is used (up to 8 KB in flight per warp).
+//   bound     : |cos32 - cos| <= 127 u (1 + |cos|) + O(u) < 1.6e-5 with u = 2^-24 when |c|^2, |m|^2 are normal fp32
+//               numbers >= 1e-30; two similarities further apart than kSimGap = 4e-5 cannot swap.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSelectWarps = 8;
+constexpr int kSelectMaxSteps = 4;          // 8 margin rows per step: n_margin <= 32
+constexpr float kSimGap = 4e-5f;
 
-__global__ void __launch_bounds__(kSelectWarps * 32) vb_coreset_select_kernel(const SelectParams p) {
-  __shared__ double s_sim[kSelectWarps][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i + 0] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// fp64 similarities of one group into sim[0 .. n_margin): a half-warp (16 lanes x 16 B) streams one row
+__device__ __noinline__ void select_sims_fp64(const __nv_bfloat16* base, int64_t stride_s, int ctok, const int32_t* mtok,
+                                              int n_margin, double* sim) {
+  const int lane = threadIdx.x & 31;
   const int half = lane >> 4, hl = lane & 15;
+  double c[8];
+  bf16x8_to_double(ld_stream(reinterpret_cast<const uint4*>(base + ctok * stride_s) + hl), c);
+  double cn = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cn = fma(c[i], c[i], cn);
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
+  const double c_norm = fmax(sqrt(cn), 1e-12);   // F.normalize eps
+  for (int m0 = 0; m0 < n_margin; m0 += 2) {
+    const int m = m0 + half;
+    double dot = 0.0, mn = 0.0;
+    if (m < n_margin) {
+      double v[8];
+      bf16x8_to_double(ld_stream(reinterpret_cast<const uint4*>(base + mtok[m] * stride_s) + hl), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dot = fma(c[i], v[i], dot);
+        mn = fma(v[i], v[i], mn);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      mn += __shfl_xor_sync(0xffffffffu, mn, o);
+    }
+    if (hl == 0 && m < n_margin) sim[m] = dot / (c_norm * fmax(sqrt(mn), 1e-12));
+  }
+}
+
+// NSTEPS = ceil(n_margin / 8) is a template parameter so that a lane holds exactly the rows it needs (16 registers
+// per step) and three CTAs fit an SM.
+template <int NSTEPS>
+__global__ void __launch_bounds__(kSelectWarps * 32, 2) vb_coreset_select_kernel(const SelectParams p) {
+  __shared__ double s_sim[kSelectWarps][32];
+  __shared__ float s_simf[kSelectWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lig = lane & 3, rg = lane >> 2;      // lane inside a row's 4-lane group, row slot 0..7 of a step
   const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G;
   const int n_p = p.n_margin - p.n_unpooled;
   const int row_len = p.G * (1 + p.n_unpooled) + p.text_len;   // kept_tok row length
 
+  // units are ordered head-fastest: neighbouring warps read the same tokens of neighbouring heads, which sit next to
+  // each other in the (B, S, H, 128) memory the projections produce (one DRAM page instead of H pages 10 KB apart)
   for (int64_t unit = static_cast<int64_t>(blockIdx.x) * kSelectWarps + warp; unit < total;
        unit += static_cast<int64_t>(gridDim.x) * kSelectWarps) {
-    const int grp = static_cast<int>(unit % p.G);
-    const int hs = static_cast<int>((unit / p.G) % p.heads);
+    const int hs = static_cast<int>(unit % p.heads);
+    const int grp = static_cast<int>((unit / p.heads) % p.G);
     const int b = static_cast<int>(unit / (static_cast<int64_t>(p.G) * p.heads));
     const int h_src = p.head_list ? p.head_list[hs] : hs;
     const __nv_bfloat16* base = p.x + b * p.stride_b + h_src * p.stride_h;
-
-    // centre row: every half-warp holds the same 8 channels per lane
     const int ctok = p.center_tok[grp];
-    double c[8];
-    bf16x8_to_double(ld_stream(reinterpret_cast<const uint4*>(base + ctok * p.stride_s) + hl), c);
-    double cn = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cn = fma(c[i], c[i], cn);
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
-    const double c_norm = fmax(sqrt(cn), 1e-12);   // F.normalize eps
-
     const int32_t* mtok = p.margin_tok + static_cast<int64_t>(grp) * p.n_margin;
-    for (int m0 = 0; m0 < p.n_margin; m0 += 2) {
-      const int m = m0 + half;
-      double dot = 0.0, mn = 0.0;
-      if (m < p.n_margin) {
-        double v[8];
-        bf16x8_to_double(ld_stream(reinterpret_cast<const uint4*>(base + mtok[m] * p.stride_s) + hl), v);
+    const int my_tok = lane < p.n_margin ? mtok[lane] : 0;       // lane i holds the token of margin i
+
+    // ---- fast path: request every row of the group, then fp32 dot products / norms ----
+    uint4 raw[NSTEPS][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          dot = fma(c[i], v[i], dot);
-          mn = fma(v[i], v[i], mn);
+    for (int s = 0; s < NSTEPS; ++s) {
+      const int m = s * 8 + rg;
+      const int tok = __shfl_sync(0xffffffffu, my_tok, m & 31);
+      if (m < p.n_margin) {
+        const uint4* row = reinterpret_cast<const uint4*>(base + tok * p.stride_s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) raw[s][j] = ld_stream(row + j * 4 + lig);
+      }
+    }
+    float c[4][8];
+    float cn = 0.f;
+    {
+      const uint4* crow = reinterpret_cast<const uint4*>(base + ctok * p.stride_s);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bf16x8_to_float(__ldg(crow + j * 4 + lig), c[j]);      // the 8 row groups read the same bytes: L1
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cn = fmaf(c[j][i], c[j][i], cn);
+      }
+      cn += __shfl_xor_sync(0xffffffffu, cn, 1);
+      cn += __shfl_xor_sync(0xffffffffu, cn, 2);
+    }
+    const bool c_ok = cn >= 1e-30f && cn < INFINITY;
+    const float c_norm = sqrtf(cn);
+#pragma unroll
+    for (int s = 0; s < NSTEPS; ++s) {
+      const int m = s * 8 + rg;
+      {
+        float dot = 0.f, mn = 0.f;
+        if (m < p.n_margin) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+            bf16x8_to_float(raw[s][j], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              dot = fmaf(c[j][i], v[i], dot);
+              mn = fmaf(v[i], v[i], mn);
+            }
+          }
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        mn += __shfl_xor_sync(0xffffffffu, mn, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        mn += __shfl_xor_sync(0xffffffffu, mn, 2);
+        if (lig == 0 && m < p.n_margin) {
+          const bool ok = c_ok && mn >= 1e-30f && mn < INFINITY;
+          const float cosv = ok ? dot / (c_norm * sqrtf(mn)) : NAN;
+          s_simf[warp][m] = cosv;
+          s_sim[warp][m] = static_cast<double>(cosv);
         }
       }
-#pragma unroll
-      for (int o = 8; o >= 1; o >>= 1) {
-        dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        mn += __shfl_xor_sync(0xffffffffu, mn, o);
+    }
+    __syncwarp();
+
+    // ---- can fp32 separate every pair?  (NaN marks a row outside the bound's range) ----
+    bool unsure = false;
+    if (lane < p.n_margin) {
+      const float mine = s_simf[warp][lane];
+      for (int j = 0; j < p.n_margin; ++j) {
+        const float d = fabsf(s_simf[warp][j] - mine);
+        unsure |= j != lane && !(d >= kSimGap);      // also true when either value is NaN
       }
-      if (hl == 0 && m < p.n_margin) s_sim[warp][m] = dot / (c_norm * fmax(sqrt(mn), 1e-12));
+    }
+    if (__any_sync(0xffffffffu, unsure)) {
+      __syncwarp();
+      select_sims_fp64(base, p.stride_s, ctok, mtok, p.n_margin, s_sim[warp]);
     }
     __syncwarp();
 
@@ -87,7 +190,7 @@ __global__ void __launch_bounds__(kSelectWarps * 32) vb_coreset_select_kernel(co
         rank += (o < mine) || (o == mine && j < lane);
       }
       const int64_t bh = static_cast<int64_t>(b) * p.heads + hs;
-      const int tok = mtok[lane];
+      const int tok = my_tok;
       if (rank < p.n_unpooled) {
         if (p.unpooled_argsort) p.unpooled_argsort[(bh * p.G + grp) * p.n_unpooled + rank] = lane;
         if (p.kept_tok) p.kept_tok[bh * row_len + p.G + static_cast<int64_t>(grp) * p.n_unpooled + rank] = tok;
@@ -112,7 +215,14 @@ int launch_coreset_select(const SelectParams& p, cudaStream_t stream) {
   if (total == 0) return VB_OK;
   const int64_t blocks_needed = (total + kSelectWarps - 1) / kSelectWarps;
   const int grid = static_cast<int>(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
-  vb_coreset_select_kernel<<<grid, kSelectWarps * 32, 0, stream>>>(p);
+  VB_REQUIRE(p.n_margin >= 1 && p.n_margin <= 8 * kSelectMaxSteps, VB_ERR_UNSUPPORTED,
+             "coreset group of %d margins not supported by the warp-level selection kernel", p.n_margin);
+  switch ((p.n_margin + 7) >> 3) {
+    case 1: vb_coreset_select_kernel<1><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
+    case 2: vb_coreset_select_kernel<2><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
+    case 3: vb_coreset_select_kernel<3><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
+    default: vb_coreset_select_kernel<4><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
+  }
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }
