@@ -168,7 +168,7 @@ typedef struct {
   uint32_t flags;
   void* workspace;
   int64_t workspace_bytes;
-  float* debug; /* bring-up only; NULL in production */
+  float* debug; /* bring-up only (read by -DVB_DEBUG_DUMP / -DVB_TIMELINE builds); NULL in production */
   /* Fused Ulysses "out" exchange over NVLink peer memory (top-1 mode only): when out_peer_count > 0, `out` is
    * ignored and the output row of token tok is stored into out_peer_ptrs[tok / out_peer_rows] at local token
    * tok % out_peer_rows, using out_stride as the strides of ONE peer buffer.  The pointers are peer-mapped device

@@ -2,6 +2,10 @@
 
 Prints, for a ladder of cases, the error of the raw score tile S = Q K^T (debug dump) and of the final output
 against an fp32 SDPA reference computed on the same device, then small-grid branch checks against the oracle.
+
+The raw-score dump is compiled only into bring-up builds of the library (it costs ~4 % in the hot loop):
+    sh vorta_b200/csrc/build_variant.sh debug -DVB_DEBUG_DUMP
+    VB_LIB_PATH=vorta_b200/lib/exp/libvb_debug.so python tests/bringup_attn.py
 """
 import os
 import sys

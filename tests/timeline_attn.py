@@ -1,4 +1,6 @@
-"""Dump and summarise the per-block clock stamps of CTA (0,0,0) (VB_TIMELINE build; perf experiment)."""
+"""Dump and summarise the per-block clock stamps of CTA 0 (perf experiment; needs the timeline build of the library):
+    sh vorta_b200/csrc/build_variant.sh timeline -DVB_TIMELINE
+    VB_LIB_PATH=vorta_b200/lib/exp/libvb_timeline.so python tests/timeline_attn.py"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

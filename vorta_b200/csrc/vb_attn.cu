@@ -317,7 +317,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         for (int c = 0; c < 2; ++c) tmem_ld32(s_addr + h * 64 + c * 32, s[c]);
         tmem_ld_wait();
         if (row == 0 && h == 0) VB_STAMP(t, j, 2);
-#ifndef VB_TIMELINE
+#if defined(VB_DEBUG_DUMP) && !defined(VB_TIMELINE)   // bring-up builds only: costs ~4 % in the product kernel
         if (p.dbg != nullptr && j == 0 && blockIdx.x == 0) {
           float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN + h * 64;   // raw scores of block 0
 #pragma unroll
@@ -442,7 +442,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         uint32_t o[32];
         tmem_ld32(o_addr + c * 32, o);
         tmem_ld_wait();
-#ifndef VB_TIMELINE
+#if defined(VB_DEBUG_DUMP) && !defined(VB_TIMELINE)   // bring-up builds only: costs ~4 % in the product kernel
         if (p.dbg != nullptr && blockIdx.x == 0) {
           float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim + h * 64;
 #pragma unroll
