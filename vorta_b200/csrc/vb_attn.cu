@@ -8,15 +8,21 @@
 //     sliding  : the <= 9 (+1 text) runs of the 3-D tile window, tile-major order
 // so the block-sparse schedule is just a different table, and masked 3-D tiles are never visited.
 //
-// Warp roles (320 threads):
-//     warps 0-3 : softmax + correction + epilogue for query tile 0 (one thread per query row / TMEM lane)
-//     warps 4-7 : same for query tile 1
-//     warp  8   : TMA producer (Q tiles once, then K/V blocks through a 5-slot ring of 32 KB)
-//     warp  9   : tcgen05.mma issuer (+ TMEM allocation)
-// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (bf16) overwrites the first 64
-// columns of its S.  S = Q K^T is an SS UMMA (both operands K-major, SWIZZLE_128B as written by TMA), O += P V is
-// a TS UMMA (P from TMEM, V from shared memory, MN-major).  While the softmax warps of one tile work on S_t(j),
-// the tensor pipe runs PV and the next QK of the other tile.
+// Warp roles (608 threads):
+//     warps 0-15 : softmax + correction + epilogue; warp = 8 t + 4 h + q: query tile t, key / channel half h, row
+//                  quarter q (TMEM lanes 32 q .. 32 q + 31) - two threads per query row
+//     warp  16   : TMA producer (Q tiles once, then K/V blocks through a 5-slot ring of 32 KB)
+//     warps 17,18: tcgen05.mma issuers, one per query tile (17 also allocates TMEM)
+// TMEM (512 columns): S [0,128) shared by the two tiles | P0 [128,192) P1 [192,256) (bf16) | O0 [256,384) O1 [384,512).
+// S = Q K^T is an SS UMMA (both operands K-major, SWIZZLE_128B as written by TMA), O += P V is a TS UMMA (P from
+// TMEM, V from shared memory, MN-major).
+//
+// Decoupled pipeline.  P does not alias S, so QK_t(j+1) does not have to wait for softmax_t(j) -> PV_t(j): it is issued
+// as soon as the softmax warps of tile t have their row maximum of block j (bar_qk_go) and the S region has been
+// loaded into registers by its previous user (bar_s_free; the region alternates strictly between the tiles).  The
+// softmax warps find S(j+1) complete when they finish block j and do not wait in steady state.  (With P aliased on S
+// and one S per tile the chain softmax -> PV -> QK was serial per tile: 1600 + 300 + 1024 cycles per block, tensor pipe
+// 61 % busy; profiles/r1g_timeline_dense16k.log vs r1l_timeline_decoupled.log.)
 #include "vb_common.cuh"
 #include "vb_ptx.cuh"
 
@@ -28,9 +34,10 @@ constexpr int kHalfBytes = kTileBytes / 2;
 constexpr int kSoftmaxWarps = 16;                  // 2 tiles x 2 column halves x 4 row quarters
 constexpr int kTmaWarp = kSoftmaxWarps;
 constexpr int kMmaWarp = kSoftmaxWarps + 1;
-constexpr int kAttnThreads = (kSoftmaxWarps + 2) * 32;
+constexpr int kMmaWarps = 2;                       // one issuer per query tile, on different schedulers
+constexpr int kAttnThreads = (kSoftmaxWarps + 1 + kMmaWarps) * 32;
 #ifndef VB_POLY_GROUPS
-#define VB_POLY_GROUPS 0x22        // groups 1 and 5 of every 8 groups of 4 keys: 1/4 of the exps on the FMA pipe (measured best of 0..5/8)
+#define VB_POLY_GROUPS 0x02        // group 1 of every 8 groups of 4 keys: 1/8 of the exps on the FMA pipe (measured best of 0, 1/8, 2/8, 3/8)
 #endif
 constexpr unsigned kPolyGroups = VB_POLY_GROUPS;
 constexpr float kRescaleThreshold = 8.0f;          // lazy rescale: tolerate 2^8 growth before touching O
@@ -45,6 +52,9 @@ struct SmemLayout {
   uint64_t bar_p_half[2];
   uint64_t bar_p_ready[2];
   uint64_t bar_o_full[2];
+  uint64_t bar_s_free;          // the shared S region has been loaded into registers by its tile's softmax warps
+  uint64_t bar_qk_go[2];        // softmax of tile t passed the trigger point of its block: QK of the next block may issue
+  uint64_t bar_pv_done[2];      // PV of tile t completed: P_t is free again and O_t is quiescent
   uint32_t tmem_base_slot;
   KvRun runs[32];
   float xchg[2][2][kBlockM];                 // row max / row sum exchange between the two threads of a row
@@ -83,11 +93,7 @@ struct BlockWalker {
 #define VB_STAMP(who, j, slot) do {} while (0)
 #endif
 
-#ifdef VB_EXP_NOMUFU            // perf experiment: softmax without the MUFU ex2 (results are garbage)
-#define VB_EXP2(x) ((x) * 0.001f)
-#else
 #define VB_EXP2(x) fast_exp2(x)
-#endif
 
 __device__ __forceinline__ int count_blocks(const KvRun* runs, int n_runs) {
   int n = 0;
@@ -148,7 +154,12 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
     }
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(&bar_slot_full[i], 1);
-      mbar_init(&bar_slot_empty[i], 1);
+      mbar_init(&bar_slot_empty[i], nq);     // one commit per query tile that consumed the slot
+    }
+    mbar_init(&sm.bar_s_free, kSoftmaxWarps / 2);        // lane 0 of the 8 warps of the loading tile
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.bar_qk_go[i], kSoftmaxWarps / 2);
+      mbar_init(&sm.bar_pv_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -193,7 +204,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp >= kMmaWarp) {
     // ======================================= MMA issuer =========================================
     // The whole warp runs this role converged and every address below is made warp-uniform, so descriptors live
     // in uniform registers and one elected lane issues; a single-lane role pays a register->uniform "waterfall"
@@ -203,79 +214,74 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
     if (nblk > 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
-      // descriptor = hi:lo; hi = SBO (1024 B) | version 1 | SWIZZLE_128B, identical for Q, K and V
       constexpr uint64_t desc_hi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
-      constexpr uint32_t lbo_k = 1u << 16;                          // K-major: LBO field = 1 (16 B, unused)
-      constexpr uint32_t lbo_v = (kHalfBytes >> 4) << 16;           // MN-major V: LBO = 16 KB between channel halves
+      constexpr uint32_t lbo_k = 1u << 16;
+      constexpr uint32_t lbo_v = (kHalfBytes >> 4) << 16;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t q_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_q) & 0x3FFFFu) >> 4, 0);
       const uint32_t kv_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_kv) & 0x3FFFFu) >> 4, 0);
-
       auto issue_qk = [&](int t, uint32_t slot) {
         const uint32_t a0 = q_lo + t * (kTileBytes >> 4) + lbo_k;
         const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_k;
-        const uint32_t d = tb + t * kBlockN;
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k) {
-          // K-major 128 B swizzled rows: 16 channels = 32 B inside the atom, 64 channels = the other half
           const uint32_t off = (k >> 2) * (kHalfBytes >> 4) + (k & 3) * 2;
-          umma_ss(d, desc_hi | (a0 + off), desc_hi | (b0 + off), idesc_qk, k > 0);
+          umma_ss(tb, desc_hi | (a0 + off), desc_hi | (b0 + off), idesc_qk, k > 0);
         }
       };
-      // PV in two halves of 64 keys, so the first can start as soon as half of P is in TMEM
       auto issue_pv = [&](int t, uint32_t slot, uint32_t accumulate, int half) {
         const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_v;
         const uint32_t d = tb + 2 * kBlockN + t * kHeadDim;
-        const uint32_t a = tb + t * kBlockN;            // P_t: packed bf16 pairs, 8 columns per 16 keys
+        const uint32_t a = tb + kBlockN + t * 64;
 #pragma unroll
         for (int kk = 0; kk < kBlockN / 32; ++kk) {
           const int k = half * (kBlockN / 32) + kk;
-          // V block [128 keys][128 channels], MN-major: 16 keys = 16 rows x 128 B = 2048 B
           umma_ts(d, a + k * 8, desc_hi | (b0 + k * (2048 >> 4)), idesc_pv, accumulate | (k > 0));
         }
       };
-
-      for (int t = 0; t < nq_u; ++t) mbar_wait(&bar_q_full[t], 0);
-      mbar_wait(&bar_slot_full[0], 0);   // K(0) is load 0
-      tc_fence_after();
-      if (elect_one()) {
-        for (int t = 0; t < nq_u; ++t) {
-          issue_qk(t, 0);
-          umma_commit(&bar_s_full[t]);
-        }
-        umma_commit(&bar_slot_empty[0]);
-      }
-      __syncwarp();
-
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t v_idx = 2 * j + 1, v_slot = v_idx % kNumSlots, v_phase = (v_idx / kNumSlots) & 1u;
-        const uint32_t k_idx = 2 * j + 2, k_slot = k_idx % kNumSlots, k_phase = (k_idx / kNumSlots) & 1u;
-        const bool more = j + 1 < nblk;
-        // operand waits first: TMA runs far ahead, so these are off the critical path; the softmax -> P hand-off
-        // below is ON it (round-1 timeline: every extra wait after p_ready costs ~100-300 cycles of tensor idle)
-        mbar_wait(&bar_slot_full[v_slot], v_phase);
-        if (more) mbar_wait(&bar_slot_full[k_slot], k_phase);
-        for (int t = 0; t < nq_u; ++t) {
-          mbar_wait(&bar_p_half[t], j & 1);
-          if (lane == 0) VB_STAMP(2 + t, j, 0);
+      // One issuer warp per query tile, on different schedulers: an issuer shares its scheduler with four busy softmax
+      // warps and crawls through the ~40 instructions between two MMA batches (measured 220-600 cycles); with two
+      // issuers one tile's gap overlaps the other tile's batch (one issuer for both tiles: 1230 TFLOP/s dense, two:
+      // 1415; a polling event loop instead of in-order suspended waits starved completely: 1167).  Each issues, in
+      // order, QK_t(0), then per block QK_t(j+1) and PV_t(j) in two halves of 64 keys.
+      // The S region alternates strictly between the tiles through bar_s_free: use number u = nq * j + t waits for
+      // completion u - 1.
+      const int t = warp - kMmaWarp;
+      if (t < nq_u) {
+        mbar_wait(&bar_q_full[t], 0);
+        auto do_qk = [&](int j) {
+          const uint32_t k_idx = 2 * j, k_slot = k_idx % kNumSlots, k_phase = (k_idx / kNumSlots) & 1u;
+          const int use = nq_u * j + t;
+          if (j > 0) mbar_wait(&sm.bar_qk_go[t], (j - 1) & 1);
+          if (use > 0) mbar_wait(&sm.bar_s_free, (use - 1) & 1);
+          mbar_wait(&bar_slot_full[k_slot], k_phase);
           tc_fence_after();
+          if (lane == 0) VB_STAMP(2 + t, j, 0);
+          if (elect_one()) {
+            issue_qk(t, k_slot);
+            umma_commit(&bar_s_full[t]);
+            umma_commit(&bar_slot_empty[k_slot]);
+          }
+          __syncwarp();
+          if (lane == 0) VB_STAMP(2 + t, j, 3);
+        };
+        do_qk(0);
+        for (int j = 0; j < nblk; ++j) {
+          const uint32_t v_idx = 2 * j + 1, v_slot = v_idx % kNumSlots, v_phase = (v_idx / kNumSlots) & 1u;
+          if (j + 1 < nblk) do_qk(j + 1);
+          mbar_wait(&bar_slot_full[v_slot], v_phase);
+          mbar_wait(&bar_p_half[t], j & 1);
+          tc_fence_after();
+          if (lane == 0) VB_STAMP(2 + t, j, 1);
           if (elect_one()) issue_pv(t, v_slot, j > 0, 0);
           __syncwarp();
           mbar_wait(&bar_p_ready[t], j & 1);
           tc_fence_after();
-          if (lane == 0) VB_STAMP(2 + t, j, 1);
           if (elect_one()) {
             issue_pv(t, v_slot, j > 0, 1);
-            if (more) {
-              issue_qk(t, k_slot);
-              umma_commit(&bar_s_full[t]);
-            } else {
-              umma_commit(&bar_o_full[t]);
-            }
-            if (t == nq_u - 1) {
-              umma_commit(&bar_slot_empty[v_slot]);
-              if (more) umma_commit(&bar_slot_empty[k_slot]);
-            }
+            umma_commit(&sm.bar_pv_done[t]);
+            umma_commit(&bar_slot_empty[v_slot]);
+            if (j == nblk - 1) umma_commit(&bar_o_full[t]);
           }
           __syncwarp();
           if (lane == 0) VB_STAMP(2 + t, j, 2);
@@ -295,7 +301,8 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
     const int pair_bar = 1 + t * 4 + q4;            // named barrier of the two warps sharing these rows
     if (t < nq && n_blocks > 0) {
       const uint32_t lane_addr = static_cast<uint32_t>(q4 << 5) << 16;
-      const uint32_t s_addr = tmem_base + lane_addr + t * kBlockN;
+      const uint32_t s_addr = tmem_base + lane_addr;                              // S region shared by both tiles
+      const uint32_t p_addr = tmem_base + lane_addr + kBlockN + t * 64 + h * 32;  // P_t: its own 64 columns
       const uint32_t o_addr = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim + h * 64;
       const float scale = p.scale_log2;
       float m_ref = 0.f, l_sum = 0.f;
@@ -307,15 +314,13 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         mbar_wait(&bar_s_full[t], j & 1);
         tc_fence_after();
         if (row == 0 && h == 0) VB_STAMP(t, j, 1);
-#ifdef VB_EXP_SKIP_SOFTMAX   // perf experiment: tensor-pipe-only throughput (results are garbage)
-        tc_fence_before();
-        mbar_arrive(h == 0 ? &bar_p_half[t] : &bar_p_ready[t]);
-        continue;
-#endif
         uint32_t s[2][32];
 #pragma unroll
         for (int c = 0; c < 2; ++c) tmem_ld32(s_addr + h * 64 + c * 32, s[c]);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.bar_s_free);      // the S region may be overwritten by the next QK
         if (row == 0 && h == 0) VB_STAMP(t, j, 2);
 #if defined(VB_DEBUG_DUMP) && !defined(VB_TIMELINE)   // bring-up builds only: costs ~4 % in the product kernel
         if (p.dbg != nullptr && j == 0 && blockIdx.x == 0) {
@@ -343,11 +348,11 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
             mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
             mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
           }
-        // row maximum over both halves; the barrier also orders "both threads hold their S values in registers"
-        // before either overwrites S with P
+        // row maximum over both halves (exchange through shared memory + a 64-thread named barrier)
         s_xchg[t][h][row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         named_bar_sync(pair_bar, 64);
         const float m_new = fmaxf(s_xchg[t][0][row], s_xchg[t][1][row]) * scale;   // block has >= 1 valid key: finite
+        if (j + 1 < n_blocks && lane == 0) mbar_arrive(&sm.bar_qk_go[t]);          // QK_t(j+1) may issue now
         if (row == 0 && h == 0) VB_STAMP(t, j, 6);
 
         if (j == 0) {
@@ -360,8 +365,10 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
               alpha = fast_exp2(m_ref - m_new);
               m_ref = m_new;
             }
-            // PV_t(j-1) completed before S_t(j) was signalled (commit order) and PV_t(j) waits for BOTH halves'
-            // arrivals: O_t is quiescent.  Each thread rescales its 64 channels.
+            // O_t must be quiescent: PV_t(j-1) may still be in flight (QK_t(j) was issued before it), PV_t(j) cannot
+            // start before BOTH halves have arrived below.  Each thread rescales its 64 channels.
+            mbar_wait(&sm.bar_pv_done[t], (j - 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
               uint32_t o[16];
@@ -404,7 +411,11 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
           if (c == 0) { asm volatile("" ::: "memory"); if (row == 0 && h == 0) VB_STAMP(t, j, 7); }
 #endif
         }
-        tmem_st32(s_addr + h * 32, pk);   // P_t(j): keys [64 h, 64 h + 64) -> 32 columns of bf16 pairs
+        if (j > 0) {                       // P_t(j-1) must have been consumed before it is overwritten
+          mbar_wait(&sm.bar_pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st32(p_addr, pk);            // P_t(j): keys [64 h, 64 h + 64) -> 32 columns of bf16 pairs
         l_sum += (sum0 + sum1) + (sum2 + sum3);
         if (row == 0 && h == 0) VB_STAMP(t, j, 3);
         tmem_st_wait();
