@@ -416,6 +416,42 @@ def test_dense_attention_independent_lengths():
         assert_attn_close(out, O.sdpa(q.float(), k.float(), v.float()))
 
 
+def _ramp_qkv(n_q, n_k, heads, step, seed):
+    """Queries along +-u, keys along u with a magnitude that grows by `step` (natural-log logit units) every 128 keys:
+    the row maximum of half of the rows jumps by more than the kernel's lazy-rescale threshold (2^8) at every key block,
+    the other half never grows (both cases inside the same warp)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(128, generator=g)
+    u = u / u.norm()
+    sign = torch.where(torch.arange(n_q) % 3 == 0, -1.0, 1.0)
+    q = sign[None, None, :, None] * u * 128 ** 0.5 + 0.05 * torch.randn((1, heads, n_q, 128), generator=g)
+    c = step * (torch.arange(n_k) // 128).float()
+    k = c[None, None, :, None] * u + 0.05 * torch.randn((1, heads, n_k, 128), generator=g)
+    v = torch.randn((1, heads, n_k, 128), generator=g)
+    return q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+
+
+def test_lazy_rescale_path_growing_logits():
+    """O is rescaled only when a row maximum grows by more than 2^8 after the first block, which random inputs never
+    do: force it at every block (the rescale must wait for the PV of the previous block that may still be in flight)."""
+    for n_q, n_k, step in ((300, 1100, 8.0), (128, 640, 20.0), (257, 300, 40.0)):
+        q, k, v = _ramp_qkv(n_q, n_k, 2, step, seed=n_q)
+        out = ops.attn_dense(to_dev_bhnd(q), to_dev_bhnd(k), to_dev_bhnd(v))
+        assert_attn_close(out, O.sdpa(q.float(), k.float(), v.float()))
+
+
+def test_lazy_rescale_path_routed_branches():
+    """Same growth through the three branches (run lists, tails, coreset unpool) against the oracle."""
+    lat, tile, win, lw = (4, 12, 16), (2, 6, 8), (3, 3, 3), (2, 3, 2)
+    S = lat[0] * lat[1] * lat[2]
+    q, k, v = _ramp_qkv(S, S, 3, 9.0, seed=21)
+    plan = ops.Plan(lat, tile, win, lw, 0.5)
+    info = O.get_group_info(lat, lw, 0.5)
+    out = ops.routed_attention(plan, to_dev_bhnd(q), to_dev_bhnd(k), to_dev_bhnd(v), branch=[0, 1, 2])
+    ref = O.routed_attention(q.float(), k.float(), v.float(), info, lat, win, tile, branch=torch.tensor([0, 1, 2]))
+    assert_attn_close(out, ref)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BASELINE-size properties (size-independent invariants; the oracle is only sampled)
 # ---------------------------------------------------------------------------------------------------------
