@@ -142,3 +142,68 @@ class _Unrouted:
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, image_rotary_emb=None,
                  **_):
         return self.proc(attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb)
+
+
+def test_wan_denoise_loop_cfg_and_routing_scores():
+    """Denoising loop of wan_pipeline_call (pipeline_wan.py:323-365) on the tiny shell: equals a hand-written loop of
+    the same forwards; guidance_scale <= 1 makes a single forward per step; routing scores come back per step."""
+    from vorta_b200.patch.pipeline import FlowMatchEulerScheduler, wan_denoise
+    wan_mod.WAN_CONFIGS["tiny"] = wan_mod.WanConfig(dim=384, heads=3, ffn_dim=512, num_layers=2, text_dim=64)
+    dev = torch.device("cuda:0")
+    model = WanDiT.build("tiny", dev, torch.bfloat16, seed=7)
+    apply_vorta_transformer(model, router_dtype=torch.float32)
+    kw = prepare_wan_self_attn_kwargs(dict(latent_shape=LAT, window_size=WIN, tile_size=TILE, lowres_window_size=LW,
+                                           lowres_reduction_rate=0.5), dev, tau_sparse=0.3)
+    g = torch.Generator().manual_seed(8)
+    noise = torch.randn((1, 16, LAT[0], 2 * LAT[1], 2 * LAT[2]), generator=g).to(dev)
+    pos = torch.randn((1, 20, 64), generator=g).to(dev)
+    neg = torch.randn((1, 20, 64), generator=g).to(dev)
+    steps, scale = 3, 5.0
+    out = wan_denoise(model, FlowMatchEulerScheduler(shift=3.0), noise.clone(), pos, neg, guidance_scale=scale,
+                      num_inference_steps=steps, self_attention_kwargs=kw, return_routing_scores=True)
+    assert out.frames.shape == noise.shape and out.frames.dtype == torch.float32
+    assert len(out.routing_scores) == steps and len(out.routing_scores[0]) == 2
+    assert tuple(out.routing_scores[0][0].shape) == (1, 3, 3)
+    # hand-written loop
+    sch = FlowMatchEulerScheduler(shift=3.0)
+    sch.set_timesteps(steps, device=dev)
+    x = noise.clone()
+    calls = 0
+    with torch.no_grad():
+        for i, t in enumerate(sch.timesteps):
+            xin, ts = x.to(torch.bfloat16), t.expand(1)
+            c = model(xin, ts, pos.to(torch.bfloat16), self_attention_kwargs=kw)[0]
+            u = model(xin, ts, neg.to(torch.bfloat16), self_attention_kwargs=kw)[0]
+            calls += 2
+            v = u + scale * (c - u)
+            x = (x.float() + (sch.sigmas[i + 1] - sch.sigmas[i]) * v.float())
+    assert torch.equal(out.frames, x)
+    assert float(sch.sigmas[-1]) == 0.0 and abs(float(sch.sigmas[0]) - 1.0) < 1e-6
+    # no CFG: one forward per step and a different trajectory
+    lat2, _ = wan_denoise(model, FlowMatchEulerScheduler(shift=3.0), noise.clone(), pos, neg, guidance_scale=1.0,
+                          num_inference_steps=steps, self_attention_kwargs=kw, return_dict=False)
+    assert lat2.shape == noise.shape and not torch.equal(lat2, out.frames)
+
+
+def test_hunyuan_denoise_loop_runs():
+    from vorta_b200.patch.pipeline import FlowMatchEulerScheduler, hunyuan_denoise
+    dev = torch.device("cuda:0")
+    cfg = HunyuanConfig(heads=3, num_layers=1, num_single_layers=1, text_embed_dim=64, pooled_projection_dim=32)
+    model = HunyuanDiT.build(cfg, dev, torch.bfloat16, seed=9)
+    modeling_hunyuan.apply_vorta_transformer(model, router_dtype=torch.float32)
+    lat, tile, win, lw = (2, 8, 8), (1, 4, 4), (3, 3, 3), (2, 2, 2)
+    kw = prepare_hunyuan_self_attn_kwargs(dict(latent_shape=lat, window_size=win, tile_size=tile,
+                                               lowres_window_size=lw, lowres_reduction_rate=0.5), dev, tau_sparse=0.3)
+    g = torch.Generator().manual_seed(10)
+    noise = torch.randn((1, 16, lat[0], 2 * lat[1], 2 * lat[2]), generator=g).to(dev)
+    text = torch.randn((1, 16, 64), generator=g).to(dev)
+    mask = torch.zeros((1, 16), dtype=torch.bool, device=dev)
+    mask[:, :9] = True
+    pooled = torch.randn((1, 32), generator=g).to(dev)
+    before = kw.get("flex_attn_mask_func")
+    out = hunyuan_denoise(model, FlowMatchEulerScheduler(shift=7.0), noise.clone(), text, mask, pooled,
+                          guidance_scale=6.0, num_inference_steps=2, self_attention_kwargs=kw,
+                          return_routing_scores=True)
+    assert out.frames.shape == noise.shape and torch.isfinite(out.frames).all()
+    assert len(out.routing_scores) == 2 and len(out.routing_scores[0]) == 2
+    assert kw.get("flex_attn_mask_func") is before        # the caller's kwargs are not mutated (deep copy, :378)

@@ -143,3 +143,20 @@ def test_balance_heads_is_a_valid_and_better_placement():
     assert balance_heads([0] * 8, costs, 4) is None        # uniform routing: contiguous is already optimal
     assert balance_heads([0, 1, 2], costs, 1) is None
     assert balance_heads([0, 1, 2], costs, 2) is None      # heads not divisible: left to the caller's error path
+
+
+def test_flow_match_euler_scheduler_cpu():
+    """Scheduler restatement used by the denoise loops: sigmas fall from 1 to 0, timesteps = 1000 sigma, an Euler step
+    along a constant velocity field integrates exactly to x0 - v."""
+    from vorta_b200.patch.pipeline import FlowMatchEulerScheduler
+    for shift in (1.0, 3.0, 7.0):
+        sch = FlowMatchEulerScheduler(shift=shift)
+        sch.set_timesteps(10)
+        assert sch.timesteps.shape == (10,) and sch.sigmas.shape == (11,)
+        assert abs(float(sch.sigmas[0]) - 1.0) < 1e-6 and float(sch.sigmas[-1]) == 0.0
+        assert bool((sch.sigmas[1:] < sch.sigmas[:-1]).all())
+        assert torch.allclose(sch.timesteps, sch.sigmas[:-1] * 1000)
+        x, v = torch.full((2, 3), 5.0), torch.full((2, 3), 2.0)
+        for t in sch.timesteps:
+            x = sch.step(v, t, x)[0]
+        assert torch.allclose(x, torch.full((2, 3), 3.0), atol=1e-5)
