@@ -183,7 +183,10 @@ def run_reference(args):
                 steps=args.steps, warmup=args.warmup, ms_per_step=value, higher_is_better=False, scaling="strong",
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=wl["name"], tile=wl["tile"], window=wl["window"],
-                            coreset_window=wl["lowres_window"], reduction_rate=wl["rate"]),
+                            coreset_window=wl["lowres_window"], reduction_rate=wl["rate"], tau_sparse=TAU_SPARSE,
+                            parallelism=f"host cpu, {cores} threads",
+                            routing="uniform 1/3 branch mix (expectation of random-init routers)",
+                            heads_per_branch_all_layers=dict(full=counts[0], coreset=counts[1], sliding=counts[2])),
                 cpu_baseline=dict(value=value, unit="ms", cores=cores, kind="port", sample=sample,
                                   per_head_ms=last),
                 e2e=dict(value=value, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
