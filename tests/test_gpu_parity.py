@@ -13,7 +13,8 @@ from oracle import vorta_oracle as O
 from vorta_b200 import _lib as L
 from vorta_b200 import ops
 from vorta_b200.attention import (HunyuanVideoFlashAttnProcessorTripleEval, HunyuanVideoFlashAttnProcessorTripleTrain,
-                                  MatchingResults, WanAttnProcessorTripleEval, WanAttnProcessorTripleTrain,
+                                  MatchingResults, WanAttnProcessor2_0, WanAttnProcessorTripleEval,
+                                  WanAttnProcessorTripleTrain,
                                   create_sliding_tile_attn_mask_func, get_group_info, pool_sequence_by_similarity,
                                   sliding_tile_flex_attn, tile_layout, unpool_sequence_by_similarity, untile_layout)
 from vorta_b200.patch import Router, route_step
@@ -281,6 +282,39 @@ def test_wan_processors_vs_reference(golden):
     bad = dict(kw, tile_size=(3, 3, 4))
     with pytest.raises(ValueError, match="does not divide latent shape"):
         ev(attn, hs, None, None, rot, tau_sparse=0.3, routing_score=mix, **bad)
+
+
+def test_wan_cross_attention_with_i2v_image_keys():
+    """Base processor, cross-attention with the I2V image-key branch (wan.py:72-76, 120-139, 154-156): the first 257
+    context tokens go through add_k_proj / norm_added_k / add_v_proj, their attention output is added to the text one
+    before the output projection.  Reference: the same dataflow in fp32 torch on the same (bf16-valued) weights."""
+    import torch.nn as nn
+    H, S, T = 2, 200, 40
+    attn32 = FX.FakeWanAttn(H, seed=41)
+    attn32.add_k_proj, attn32.add_v_proj = nn.Linear(H * 128, H * 128), nn.Linear(H * 128, H * 128)
+    attn32.norm_added_k = nn.RMSNorm(H * 128, eps=1e-6)
+    FX.fill_module_(attn32, 41)
+    attn32 = attn32.to(torch.bfloat16).float()                       # bf16-representable weights on both sides
+    attn = FX.FakeWanAttn(H, seed=41)
+    attn.add_k_proj, attn.add_v_proj = nn.Linear(H * 128, H * 128), nn.Linear(H * 128, H * 128)
+    attn.norm_added_k = nn.RMSNorm(H * 128, eps=1e-6)
+    attn.load_state_dict(attn32.state_dict())
+    attn = attn.to(dev(), torch.bfloat16)
+    hs = FX.det_tensor((1, S, H * 128), 42).to(torch.bfloat16)
+    ctx = FX.det_tensor((1, 257 + T, H * 128), 43).to(torch.bfloat16)
+    with torch.no_grad():
+        out = WanAttnProcessor2_0()(attn, hs.to(dev()), ctx.to(dev()), None, None)
+        a, x, c = attn32, hs.float(), ctx.float()
+        img, txt = c[:, :257], c[:, 257:]
+
+        def heads(t):
+            return t.unflatten(2, (H, -1)).transpose(1, 2)
+
+        q, k, v = heads(a.norm_q(a.to_q(x))), heads(a.norm_k(a.to_k(txt))), heads(a.to_v(txt))
+        ki, vi = heads(a.norm_added_k(a.add_k_proj(img))), heads(a.add_v_proj(img))
+        o = O.sdpa(q, k, v) + O.sdpa(q, ki, vi)
+        ref = a.to_out[0](o.transpose(1, 2).flatten(2, 3))
+    assert_attn_close(out, ref, cos_min=0.999, max_abs=2e-2 * max(ref.abs().max().item(), 1.0))
 
 
 def _hy_plan():
