@@ -118,7 +118,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
   KvRun* s_runs = sm.runs;
   float (*s_xchg)[2][kBlockM] = sm.xchg;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: role / address math in uniform registers
   const int lane = threadIdx.x & 31;
   // linear CTA index -> (segment, pair, head, batch); segments are laid out longest CTAs first by the host
   int seg_idx = 0;
