@@ -33,6 +33,10 @@ WORKLOADS = {
                   lowres_window=(3, 3, 2), rate=0.5, text_tokens=512,
                   name="Wan2.1-T2V-1.3B 480p x81f (21x30x52 = 32,760 tokens, 12 heads, 30 blocks), one denoise step"),
 }
+# contract test only (tests/test_bench_contract.py): tiny grid, 4 heads, 2 blocks; never a reported number
+WORKLOADS["tiny"] = dict(model="wan-contract-test", latent=(4, 6, 8), tile=(2, 3, 4), window=(3, 3, 3),
+                         lowres_window=(2, 3, 2), rate=0.5, text_tokens=16,
+                         name="CONTRACT TEST ONLY: 2-block 4-head Wan shell, 4x6x8 = 192 tokens")
 WORKLOADS["hunyuan"] = dict(model="hunyuanvideo", latent=(33, 45, 80), tile=(3, 9, 16), window=(3, 3, 3),
                             lowres_window=(3, 3, 2), rate=0.5, text_tokens=256, text_valid=64,
                             name="HunyuanVideo 720p x129f (33x45x80 = 118,800 video tokens + 256 text (64 valid), 24 heads, "

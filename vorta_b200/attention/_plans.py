@@ -4,6 +4,7 @@ from __future__ import annotations
 from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
+import torch
 
 from .. import ops
 
@@ -28,7 +29,9 @@ def infer_lowres_window(group_info, latent_shape: Sequence[int]) -> Tuple[int, i
 
 def get_plan(latent_shape, tile_size, window_size, lowres_window, n_unpooled: int, text_len: int = 0,
              text_valid: int = 0) -> ops.Plan:
-    key = (_t3(latent_shape), _t3(tile_size), _t3(window_size), _t3(lowres_window), int(n_unpooled), int(text_len))
+    # the plan's device tables live on the device that is current when it is created
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    key = (_t3(latent_shape), _t3(tile_size), _t3(window_size), _t3(lowres_window), int(n_unpooled), int(text_len), dev)
     plan = _CACHE.get(key)
     if plan is None:
         plan = ops.Plan(key[0], key[1], key[2], key[3], n_unpooled=int(n_unpooled), text_len=int(text_len),

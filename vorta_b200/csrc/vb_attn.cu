@@ -548,11 +548,13 @@ int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int6
 
 // `params.seg[i].cta_begin` must already hold the prefix sums; n_ctas = total over the segments.
 int launch_attn(const AttnTmaps& tmaps, const AttnParams& params, int n_ctas, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};      // the attribute is per device
+  int dev = 0;
+  VB_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     VB_CUDA_OK(cudaFuncSetAttribute(vb_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmemBytes));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (n_ctas == 0) return VB_OK;
   vb_attn_fwd_kernel<<<static_cast<unsigned>(n_ctas), kAttnThreads, kAttnSmemBytes, stream>>>(tmaps, params);

@@ -40,6 +40,8 @@ class WanConfig:
 WAN_CONFIGS = {
     "wan2.1-t2v-1.3b": WanConfig(dim=1536, heads=12, ffn_dim=8960, num_layers=30),
     "wan2.1-t2v-14b": WanConfig(dim=5120, heads=40, ffn_dim=13824, num_layers=40),
+    # not a real model: a 2-block, 4-head shell for the contract test of bench.py (tests/test_bench_contract.py)
+    "wan-contract-test": WanConfig(dim=512, heads=4, ffn_dim=1024, num_layers=2, text_dim=64),
 }
 
 
