@@ -317,6 +317,21 @@ def test_wan_cross_attention_with_i2v_image_keys():
     assert_attn_close(out, ref, cos_min=0.999, max_abs=2e-2 * max(ref.abs().max().item(), 1.0))
 
 
+def test_blend_mode_refuses_to_cut_the_router_gradient():
+    """The Train blend is how the reference trains its routers (wan.py:296-300).  There is no backward kernel yet:
+    asking for one must fail loudly instead of returning a result whose gradient is silently missing."""
+    lat, tile, win, lw = (4, 6, 8), (2, 3, 4), (3, 3, 3), (2, 3, 2)
+    plan = ops.Plan(lat, tile, win, lw, 0.5)
+    g = torch.Generator().manual_seed(3)
+    q, k, v = (to_dev_bhnd(torch.randn((1, 2, plan.seq_len, 128), generator=g)) for _ in range(3))
+    w = torch.softmax(torch.randn((1, 2, 3), generator=g), -1).to(dev()).requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="no backward pass"):
+        ops.routed_attention(plan, q, k, v, weights=w)
+    with torch.no_grad():
+        out = ops.routed_attention(plan, q, k, v, weights=w)
+    assert torch.isfinite(out.float()).all()
+
+
 def _hy_plan():
     c = FX.HUNYUAN_CASE
     return ops.Plan(c["latent"], c["tile"], c["window"], c["lowres_window"], c["rate"], text_len=c["text_len"],

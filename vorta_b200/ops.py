@@ -166,6 +166,12 @@ def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
     args.batch, args.heads = B, H
     keep = []
     if weights is not None:
+        if weights.requires_grad and torch.is_grad_enabled():
+            # the reference trains the routers through this blend (wan.py:296-300, scripts/wan/train_one_step.py);
+            # the backward of the attention kernels is not built, so refuse instead of
+            # silently cutting the gradient
+            raise NotImplementedError("vorta_b200: routed attention has no backward pass yet; run the Train "
+                                      "processors under torch.no_grad() or detach the routing scores")
         w = weights.detach().to(device="cpu", dtype=torch.float32).contiguous()
         if tuple(w.shape) != (B, H, 3):
             raise ValueError(f"weights must be (B, H, 3), got {tuple(w.shape)}")
