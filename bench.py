@@ -237,14 +237,14 @@ def make_step(model, wl, device, kw):
     """Returns call(latents, timestep, text) -> model outputs for the workload's model family."""
     import torch
     if wl["model"] != "hunyuanvideo":
-        return lambda lat, ts, txt, **extra: model(lat, ts, txt, self_attention_kwargs=kw, **extra)
+        return lambda lat, ts, txt, **extra: model(lat, ts, txt, self_attention_kwargs=kw, return_dict=False, **extra)
     g = torch.Generator().manual_seed(99)
     mask = torch.zeros((1, wl["text_tokens"]), dtype=torch.bool, device=device)
     mask[:, :wl["text_valid"]] = True
     pooled = torch.randn((1, model.config.pooled_projection_dim), generator=g).to(device, torch.bfloat16)
     guidance = torch.tensor([6000.0], device=device)
     return lambda lat, ts, txt, **extra: model(lat, ts, txt, mask, pooled, guidance, self_attention_kwargs=dict(kw),
-                                               **extra)
+                                               return_dict=False, **extra)
 
 
 def time_steps(fn, steps, warmup, dist_on, profile=False):
@@ -304,7 +304,7 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
 
     # routing mix of this run (one untimed forward)
     with torch.no_grad():
-        _, scores = call(lat_d, ts_d, txt_d, return_routing_scores=True)
+        scores = call(lat_d, ts_d, txt_d, return_routing_scores=True)[4]      # reference 5-tuple
     branches = [s[0].float().argmax(-1).tolist() for s in scores]
     counts = branch_counts(branches)
 

@@ -71,8 +71,10 @@ def test_wan_dit_step_matches_torch_reference():
         for li, blk in enumerate(model.blocks):
             blk.router.linear.bias.copy_(torch.tensor([[3., 0., 0.], [0., 3., 0.], [0., 0., 3.]]).roll(li, 0).flatten())
     with torch.no_grad():
-        out, scores = model(latents.to(dev, torch.bfloat16), ts.to(dev), text.to(dev, torch.bfloat16),
-                            self_attention_kwargs=kw, return_routing_scores=True)
+        res = model(latents.to(dev, torch.bfloat16), ts.to(dev), text.to(dev, torch.bfloat16),
+                    self_attention_kwargs=kw, return_routing_scores=True)
+    out, scores = res.sample, res.routing_scores                    # RoutedTransformerModelOutput (outputs.py:8-14)
+    assert res.reg_loss is None and res[0] is out and len(res.to_tuple()) == 2
     branches = [s[0].float().argmax(-1).tolist() for s in scores]
     assert sorted(set(sum(branches, []))) == [0, 1, 2]
     # reference: same weights (bf16 values) in fp32 on the CPU
@@ -113,8 +115,10 @@ def test_hunyuan_dit_step_runs_and_respects_routing():
             for blk in blocks:
                 blk.router.linear.weight.zero_()
                 blk.router.linear.bias.copy_(torch.tensor(bias).flatten())
-            return model(x, ts, text, mask, pooled, guidance, self_attention_kwargs=dict(kw),
-                         return_routing_scores=True)
+            res = model(x, ts, text, mask, pooled, guidance, self_attention_kwargs=dict(kw),
+                        return_routing_scores=True, return_dict=False)
+            assert len(res) == 5 and res[1] is None and res[2] is None and res[3] is None      # reference 5-tuple
+            return res[0], res[4]
 
     out_mix, scores = run([[4., 0., 0.], [0., 4., 0.], [0., 0., 4.]])
     assert out_mix.shape == x.shape and torch.isfinite(out_mix.float()).all()
@@ -128,7 +132,7 @@ def test_hunyuan_dit_step_runs_and_respects_routing():
     with torch.no_grad():
         for blk in blocks:
             blk.attn.set_processor(_Unrouted(blk.attn.processor))
-        out_plain = model(x, ts, text, mask, pooled, guidance, self_attention_kwargs=dict(kw))[0]
+        out_plain = model(x, ts, text, mask, pooled, guidance, self_attention_kwargs=dict(kw)).sample
     assert torch.equal(out_full, out_plain)
     assert not torch.equal(out_mix, out_full)
 
@@ -173,7 +177,7 @@ def test_wan_denoise_loop_cfg_and_routing_scores():
         for i, t in enumerate(sch.timesteps):
             xin, ts = x.to(torch.bfloat16), t.expand(1)
             c = model(xin, ts, pos.to(torch.bfloat16), self_attention_kwargs=kw)[0]
-            u = model(xin, ts, neg.to(torch.bfloat16), self_attention_kwargs=kw)[0]
+            u = model(xin, ts, neg.to(torch.bfloat16), self_attention_kwargs=kw, return_dict=False)[0]
             calls += 2
             v = u + scale * (c - u)
             x = (x.float() + (sch.sigmas[i + 1] - sch.sigmas[i]) * v.float())
@@ -207,3 +211,32 @@ def test_hunyuan_denoise_loop_runs():
     assert out.frames.shape == noise.shape and torch.isfinite(out.frames).all()
     assert len(out.routing_scores) == 2 and len(out.routing_scores[0]) == 2
     assert kw.get("flex_attn_mask_func") is before        # the caller's kwargs are not mutated (deep copy, :378)
+
+
+def test_wan_forward_reference_return_structure_and_losses():
+    """Return structure of wan_transformer_3d_routed_forward (modeling_wan.py:174-186) and the router-training
+    losses in the forward direction (:109-171) with the Train processors: L2 on the full-attention score summed over
+    blocks, hidden / last layer distillation against the un-routed blocks."""
+    wan_mod.WAN_CONFIGS["tiny"] = wan_mod.WanConfig(dim=384, heads=3, ffn_dim=512, num_layers=2, text_dim=64)
+    dev = torch.device("cuda:0")
+    model = WanDiT.build("tiny", dev, torch.bfloat16, seed=11)
+    apply_vorta_transformer(model, train_router=True, router_dtype=torch.float32)
+    kw = prepare_wan_self_attn_kwargs(dict(latent_shape=LAT, window_size=WIN, tile_size=TILE, lowres_window_size=LW,
+                                           lowres_reduction_rate=0.5), dev)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn((1, 16, LAT[0], 2 * LAT[1], 2 * LAT[2]), generator=g).to(dev, torch.bfloat16)
+    text = torch.randn((1, 20, 64), generator=g).to(dev, torch.bfloat16)
+    ts = torch.tensor([431.0], device=dev)
+    with torch.no_grad():
+        res = model(x, ts, text, self_attention_kwargs=kw, return_losses=True, reture_hidden_layer_distill_loss=True,
+                    return_routing_scores=True)
+        tup = model(x, ts, text, self_attention_kwargs=kw, return_dict=False)
+    assert len(tup) == 5 and tup[1] is None and tup[2] is None and tup[3] is None and tup[4] == []
+    assert torch.equal(tup[0], res.sample)
+    want_reg = sum(torch.square(s[:, :, 0].float()).mean() for s in res.routing_scores)
+    assert abs(float(res.reg_loss) - float(want_reg)) < 2e-3 * float(want_reg)      # squared in the router's bf16 output dtype
+    assert float(res.last_layer_distill_loss) > 0 and float(res.hidden_layer_distill_loss) > 0
+    assert all(s.device.type == "cpu" and tuple(s.shape) == (1, 3, 3) for s in res.routing_scores)
+    # training through the blend is refused loudly (no attention backward yet)
+    with pytest.raises(NotImplementedError):
+        model(x, ts, text, self_attention_kwargs=kw)

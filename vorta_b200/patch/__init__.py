@@ -4,4 +4,5 @@ from .utils import (Pixel2TokenFactory, hunyuan_pixel2token, prepare_hunyuan_sel
 from .modeling_wan import (apply_sp_flashattn_transformer, apply_vorta_transformer, load_router_checkpoint,
                            wan_block_routed_forward, wan_rope_forward, wan_transformer_3d_routed_forward)
 from . import modeling_hunyuan, modeling_wan
-from .pipeline import FlowMatchEulerScheduler, VideoPipelineOutput, hunyuan_denoise, wan_denoise
+from .outputs import RoutedTransformerModelOutput, VideoPipelineOutput
+from .pipeline import FlowMatchEulerScheduler, hunyuan_denoise, wan_denoise

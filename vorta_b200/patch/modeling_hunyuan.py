@@ -3,8 +3,8 @@
 hunyuan_dual_block_routed_forward :524-590, hunyuan_rope_forward :593-618, hunyuan_combined_embedding_forward :621-645).
 
 Same design deltas as ``modeling_wan.py``: one router launch per step (the routers read the clean timestep embedding
-only, :491/:555/:645), token sharding under Ulysses (text tokens replicated), fused elementwise passes, no training
-losses.  The per-prompt sliding-tile schedule needs no BlockMask rebuild (:232-241): the valid text length is a field
+only, :491/:555/:645), token sharding under Ulysses (text tokens replicated), fused elementwise passes, training
+losses in the forward direction only.  The per-prompt sliding-tile schedule needs no BlockMask rebuild (:232-241): the valid text length is a field
 of the plan.
 """
 from __future__ import annotations
@@ -13,12 +13,14 @@ import os
 from typing import Any, Dict, Optional, Tuple
 
 import torch
+import torch.nn.functional as F
 
 from .. import ops
 from ..attention import (HunyuanVideoFlashAttnProcessor, HunyuanVideoFlashAttnProcessorTripleEval,
                          HunyuanVideoFlashAttnProcessorTripleTrain)
 from ..ulysses import SP_STATE, all_gather
-from .modeling_wan import load_router_checkpoint
+from .modeling_wan import accumulate_loss, load_router_checkpoint
+from .outputs import RoutedTransformerModelOutput
 from .router import Router, route_step
 
 
@@ -116,10 +118,13 @@ def hunyuan_single_block_routed_forward(self, hidden_states, encoder_hidden_stat
 def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor,
                                           encoder_hidden_states: torch.Tensor, encoder_attention_mask: torch.Tensor,
                                           pooled_projections: torch.Tensor, guidance: Optional[torch.Tensor] = None,
-                                          attention_kwargs=None, return_dict: bool = False,
+                                          attention_kwargs=None, return_dict: bool = True,
                                           self_attention_kwargs: Optional[Dict[str, Any]] = None,
+                                          return_losses: bool = False, reture_hidden_layer_distill_loss: bool = False,
                                           return_routing_scores: bool = False):
-    """One DiT forward = one denoise step (dataflow of :165-449 without the training losses)."""
+    """One DiT forward = one denoise step: signature, dataflow and return structure of :165-449
+    (``return_dict=False`` -> ``(sample, reg_loss, last_layer_distill_loss, hidden_layer_distill_loss,
+    routing_scores)``); ``return_losses`` evaluates the router-training losses in the forward direction only."""
     batch_size, _, num_frames, height, width = hidden_states.shape
     p, p_t = self.config.patch_size, self.config.patch_size_t
     ppf, pph, ppw = num_frames // p_t, height // p, width // p
@@ -143,28 +148,47 @@ def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, tim
     tau = kwargs.get("tau_sparse")
     blocks = list(self.transformer_blocks) + list(self.single_transformer_blocks)
     eval_mode = isinstance(blocks[0].attn.processor, HunyuanVideoFlashAttnProcessorTripleEval)
+    if not eval_mode and torch.is_grad_enabled() and any(q.requires_grad for q in blocks[0].router.parameters()):
+        # the Train processors exist to fit the routers; that needs the backward of the attention kernels
+        raise NotImplementedError("vorta_b200: router training is not supported yet (no attention backward); run the "
+                                  "Train processors under torch.no_grad()")
     scores, branches = route_step([b.router for b in blocks], clean_emb, tau if eval_mode else None)
-    routing_scores = []
+    reg_loss = hidden_layer_distill_loss = last_layer_distill_loss = None
+    ref_hidden_states = hidden_states.detach().clone() if return_losses else None
+    ref_encoder_hidden_states = encoder_hidden_states.detach().clone() if return_losses else None
     for i, block in enumerate(blocks):
         score_i = scores[i].to(temb.dtype)
         hidden_states, encoder_hidden_states, _ = block(
             hidden_states, encoder_hidden_states, temb, attention_mask, image_rotary_emb, token_replace_emb, 0,
             use_original_attn=False, self_attention_kwargs=kwargs, clean_timesteps_emb=clean_emb,
             routing_score=score_i, branch=branches[i] if eval_mode else None)
-        if return_routing_scores:
-            routing_scores.append(score_i)
+        if return_losses:
+            with torch.no_grad():                          # reference branch: the un-routed block (:357-368)
+                ref_hidden_states, ref_encoder_hidden_states, _ = block(
+                    ref_hidden_states, ref_encoder_hidden_states, temb, attention_mask, image_rotary_emb,
+                    token_replace_emb, 0, use_original_attn=True)
+            reg_loss = accumulate_loss(reg_loss, torch.square(score_i[:, :, 0]).mean().float())
+            if reture_hidden_layer_distill_loss:
+                hidden_layer_distill_loss = accumulate_loss(
+                    hidden_layer_distill_loss, F.mse_loss(ref_hidden_states.float(), hidden_states.float()))
+    routing_scores = list(scores.detach().to(temb.dtype).cpu().unbind(0)) if return_routing_scores else []
 
     scale, shift = self.norm_out.modulation(temb)
-    hidden_states = ops.ln_modulate(hidden_states, None, None, scale, shift, 1e-6)
-    hidden_states = self.proj_out(hidden_states)
+    hidden_states = self.proj_out(ops.ln_modulate(hidden_states, None, None, scale, shift, 1e-6))
+    if return_losses:
+        with torch.no_grad():
+            ref_hidden_states = self.proj_out(ops.ln_modulate(ref_hidden_states, None, None, scale, shift, 1e-6))
+        last_layer_distill_loss = F.mse_loss(ref_hidden_states.float(), hidden_states.float())
     if SP_STATE.enabled:
         hidden_states = all_gather(hidden_states, dim=1)
     hidden_states = hidden_states.reshape(batch_size, ppf, pph, ppw, -1, p_t, p, p)
     hidden_states = hidden_states.permute(0, 4, 1, 5, 2, 6, 3, 7)
     output = hidden_states.flatten(6, 7).flatten(4, 5).flatten(2, 3)
-    if return_routing_scores:
-        return output, routing_scores
-    return (output,) if not return_dict else {"sample": output}
+    if not return_dict:
+        return (output, reg_loss, last_layer_distill_loss, hidden_layer_distill_loss, routing_scores)
+    return RoutedTransformerModelOutput(sample=output, reg_loss=reg_loss, last_layer_distill_loss=last_layer_distill_loss,
+                                        hidden_layer_distill_loss=hidden_layer_distill_loss,
+                                        routing_scores=routing_scores)
 
 
 def apply_vorta_transformer(model, train_router: bool = False, checkpoint_file: Optional[os.PathLike] = None,

@@ -7,7 +7,8 @@ Differences from the reference, by design:
   modeling_wan.py:215) and their top-1 decisions reach the host in one copy, instead of one sync per block;
 * under Ulysses the sequence is sharded by TOKENS inside the forward (the reference shards frames in the
   pipeline, pipeline_wan.py:120-122), and the RoPE table is narrowed per rank in the processor (wan.py:97);
-* the router-training losses of the reference forward (reg / distillation) are out of scope.
+* the router-training losses of the reference forward (reg / distillation) are evaluated in the forward direction
+  only; training through them needs the attention backward kernels, which do not exist yet.
 """
 from __future__ import annotations
 
@@ -15,10 +16,12 @@ import os
 from typing import Any, Dict, Optional
 
 import torch
+import torch.nn.functional as F
 
 from .. import ops
 from ..attention import WanAttnProcessor2_0, WanAttnProcessorTripleEval, WanAttnProcessorTripleTrain
 from ..ulysses import SP_STATE, all_gather
+from .outputs import RoutedTransformerModelOutput
 from .router import Router, route_step
 
 
@@ -70,19 +73,27 @@ def wan_block_routed_forward(self, hidden_states, encoder_hidden_states, temb, r
 def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor,
                                       encoder_hidden_states: torch.Tensor,
                                       encoder_hidden_states_image: Optional[torch.Tensor] = None,
-                                      return_dict: bool = False, attention_kwargs=None,
+                                      return_dict: bool = True, attention_kwargs=None,
                                       self_attention_kwargs: Optional[Dict[str, Any]] = None,
+                                      return_losses: bool = False, reture_hidden_layer_distill_loss: bool = False,
                                       return_routing_scores: bool = False):
-    """One DiT forward = one denoise step (dataflow of modeling_wan.py:38-192 without the training losses)."""
+    """One DiT forward = one denoise step: signature, dataflow and return structure of modeling_wan.py:38-192
+    (``reture_…`` is the reference's spelling).  ``return_dict=False`` gives the reference's 5-tuple
+    ``(sample, reg_loss, last_layer_distill_loss, hidden_layer_distill_loss, routing_scores)``.
+    ``return_losses`` evaluates the router-training losses of :109-171 in the forward direction (L2 on the
+    full-attention score, distillation against the un-routed blocks run without gradient); their backward through the
+    attention kernels does not exist yet."""
     batch_size, _, num_frames, height, width = hidden_states.shape
     p_t, p_h, p_w = self.config.patch_size
     ppf, pph, ppw = num_frames // p_t, height // p_h, width // p_w
 
     rotary_emb = self.rope(hidden_states)
     hidden_states = self.patch_embedding(hidden_states).flatten(2).transpose(1, 2)
-    temb, timestep_proj, encoder_hidden_states, _ = self.condition_embedder(
+    temb, timestep_proj, encoder_hidden_states, encoder_hidden_states_image = self.condition_embedder(
         timestep, encoder_hidden_states, encoder_hidden_states_image)
     timestep_proj = timestep_proj.unflatten(1, (6, -1))
+    if encoder_hidden_states_image is not None:           # I2V: [257 image tokens | text tokens] (:83-84)
+        encoder_hidden_states = torch.concat([encoder_hidden_states_image, encoder_hidden_states], dim=1)
 
     if SP_STATE.enabled:        # token sharding: S / P contiguous tokens per rank
         s_loc = hidden_states.shape[1] // SP_STATE.sp_size
@@ -92,28 +103,52 @@ def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timeste
     tau = kwargs.get("tau_sparse")
     eval_mode = isinstance(self.blocks[0].attn1.processor, WanAttnProcessorTripleEval)
     # routing of the whole step in one launch: it depends on temb only
+    if not eval_mode and torch.is_grad_enabled() and any(q.requires_grad for q in self.blocks[0].router.parameters()):
+        # the Train processors exist to fit the routers; that needs the backward of the attention kernels
+        raise NotImplementedError("vorta_b200: router training is not supported yet (no attention backward); run the "
+                                  "Train processors under torch.no_grad()")
     scores, branches = route_step([b.router for b in self.blocks], temb, tau if eval_mode else None)
-    routing_scores = []
+    reg_loss = hidden_layer_distill_loss = last_layer_distill_loss = None
+    ref_hidden_states = hidden_states.detach().clone() if return_losses else None
     for i, block in enumerate(self.blocks):
         score_i = scores[i].to(temb.dtype)
         hidden_states, _ = block(hidden_states, encoder_hidden_states, timestep_proj, rotary_emb,
                                  temb_before_proj=temb, use_original_attn=False, self_attention_kwargs=kwargs,
                                  routing_score=score_i, branch=branches[i] if eval_mode else None)
-        if return_routing_scores:
-            routing_scores.append(score_i)
+        if return_losses:
+            with torch.no_grad():                          # reference branch: the un-routed block (:122-128)
+                ref_hidden_states, _ = block(ref_hidden_states, encoder_hidden_states, timestep_proj, rotary_emb,
+                                             temb_before_proj=temb, use_original_attn=True)
+            reg_loss = accumulate_loss(reg_loss, torch.square(score_i[:, :, 0]).mean().float())      # :131-132
+            if reture_hidden_layer_distill_loss:
+                hidden_layer_distill_loss = accumulate_loss(
+                    hidden_layer_distill_loss, F.mse_loss(ref_hidden_states.float(), hidden_states.float()))
+    # one device -> host copy for the whole step (the reference copies per block, :119-120)
+    routing_scores = list(scores.detach().to(temb.dtype).cpu().unbind(0)) if return_routing_scores else []
 
     shift, scale = ((self.scale_shift_table.float() + temb.float().unsqueeze(1))).unbind(dim=1)
-    hidden_states = ops.ln_modulate(hidden_states, None, None, scale.contiguous(), shift.contiguous(),
-                                    self.norm_out.eps)
-    hidden_states = self.proj_out(hidden_states)
+    shift, scale = shift.contiguous(), scale.contiguous()
+    hidden_states = self.proj_out(ops.ln_modulate(hidden_states, None, None, scale, shift, self.norm_out.eps))
+    if return_losses:
+        with torch.no_grad():
+            ref_hidden_states = self.proj_out(ops.ln_modulate(ref_hidden_states, None, None, scale, shift,
+                                                              self.norm_out.eps))
+        last_layer_distill_loss = F.mse_loss(ref_hidden_states.float(), hidden_states.float())      # :165-171
     if SP_STATE.enabled:
         hidden_states = all_gather(hidden_states, dim=1)
     hidden_states = hidden_states.reshape(batch_size, ppf, pph, ppw, p_t, p_h, p_w, -1)
     hidden_states = hidden_states.permute(0, 7, 1, 4, 2, 5, 3, 6)
     output = hidden_states.flatten(6, 7).flatten(4, 5).flatten(2, 3)
-    if return_routing_scores:
-        return output, routing_scores
-    return (output,) if not return_dict else {"sample": output}
+    if not return_dict:
+        return (output, reg_loss, last_layer_distill_loss, hidden_layer_distill_loss, routing_scores)
+    return RoutedTransformerModelOutput(sample=output, reg_loss=reg_loss, last_layer_distill_loss=last_layer_distill_loss,
+                                        hidden_layer_distill_loss=hidden_layer_distill_loss,
+                                        routing_scores=routing_scores)
+
+
+def accumulate_loss(current_loss, new_loss):
+    """vorta/utils/misc.py:91-92."""
+    return new_loss if current_loss is None else current_loss + new_loss
 
 
 def load_router_checkpoint(checkpoint_file: os.PathLike, model) -> None:

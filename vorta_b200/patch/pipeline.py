@@ -18,19 +18,12 @@ with its all-gathered seed (``pipeline_wan.py:50-56``).
 from __future__ import annotations
 
 from copy import deepcopy
-from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 
 from ..attention import create_sliding_tile_attn_mask_func
-
-
-@dataclass
-class VideoPipelineOutput:
-    """``vorta/patch/outputs.py:17-30``: denoised latents (``output_type="latent"``) and routing scores per step."""
-    frames: torch.Tensor
-    routing_scores: Optional[List[List[torch.Tensor]]] = None
+from .outputs import VideoPipelineOutput
 
 
 class FlowMatchEulerScheduler:
@@ -90,9 +83,9 @@ def wan_denoise(transformer, scheduler, latents: torch.Tensor, prompt_embeds: to
         out = transformer(hidden_states=latent_model_input, timestep=timestep, encoder_hidden_states=prompt_embeds,
                           attention_kwargs=attention_kwargs, return_dict=False,
                           self_attention_kwargs=self_attention_kwargs, return_routing_scores=return_routing_scores)
-        noise_pred = out[0]
+        noise_pred, _, _, _, routing_score = out                                            # pipeline_wan.py:331
         if return_routing_scores:
-            routing_scores.append(out[1])
+            routing_scores.append(routing_score)
         if do_cfg:
             noise_uncond = transformer(hidden_states=latent_model_input, timestep=timestep,
                                        encoder_hidden_states=negative_prompt_embeds, attention_kwargs=attention_kwargs,
@@ -141,9 +134,9 @@ def hunyuan_denoise(transformer, scheduler, latents: torch.Tensor, prompt_embeds
                           encoder_attention_mask=prompt_attention_mask, pooled_projections=pooled_prompt_embeds,
                           guidance=guidance, attention_kwargs=attention_kwargs, return_dict=False,
                           self_attention_kwargs=kwargs, return_routing_scores=return_routing_scores)
-        noise_pred = out[0]
+        noise_pred, _, _, _, routing_score = out                                            # pipeline_hunyuan.py:408
         if return_routing_scores:
-            routing_scores.append(out[1])
+            routing_scores.append(routing_score)
         if do_true_cfg:
             neg = transformer(hidden_states=latent_model_input, timestep=timestep,
                               encoder_hidden_states=negative_prompt_embeds.to(dtype),
