@@ -160,3 +160,44 @@ def test_flow_match_euler_scheduler_cpu():
         for t in sch.timesteps:
             x = sch.step(v, t, x)[0]
         assert torch.allclose(x, torch.full((2, 3), 3.0), atol=1e-5)
+
+
+def test_top1_routing_matches_reference_rule():
+    """wan.py:396-400: top-1 expert of the FIRST sample per head; below tau_sparse -> full attention (0)."""
+    from vorta_b200.attention.wan import _top1_branches
+    score = torch.tensor([[[0.5, 0.3, 0.2], [0.2, 0.45, 0.35], [0.1, 0.2, 0.7], [0.34, 0.33, 0.33]],
+                          [[0.0, 1.0, 0.0]] * 4])                       # second sample is ignored
+    assert _top1_branches(score, 0.3) == [0, 1, 2, 0]
+    assert _top1_branches(score, 0.5) == [0, 0, 2, 0]                    # 0.45 < tau -> full
+    assert _top1_branches(score, None) == [0, 1, 2, 0]
+    assert _top1_branches(score, 0.75) == [0, 0, 0, 0]
+
+
+def test_local_heads_follow_the_head_table():
+    from vorta_b200.ulysses import SP_STATE, local_heads
+    vals = list("abcdefgh")
+    assert local_heads(vals, 8) == vals                                  # SP disabled: untouched
+    SP_STATE._enabled, SP_STATE._sp_size, old_rank = True, 4, SP_STATE.__dict__.get("_group_local_rank")
+    try:
+        SP_STATE._group_local_rank = 2
+        if SP_STATE.group_local_rank != 2:
+            pytest.skip("SP_STATE does not expose a settable local rank")
+        assert local_heads(vals, 8) == ["e", "f"]
+        assert local_heads(vals, 8, head_at=[0, 7, 1, 6, 2, 5, 3, 4]) == ["c", "f"]
+    finally:
+        SP_STATE._enabled, SP_STATE._sp_size = False, 1
+        if old_rank is not None:
+            SP_STATE._group_local_rank = old_rank
+
+
+def test_routed_output_container_behaves_like_base_output():
+    """vorta/patch/outputs.py: attribute, key and index access; to_tuple skips None fields (diffusers BaseOutput)."""
+    from vorta_b200.patch import RoutedTransformerModelOutput, VideoPipelineOutput
+    x = torch.zeros(2)
+    out = RoutedTransformerModelOutput(sample=x, routing_scores=[])
+    assert out.sample is x and out["sample"] is x and out[0] is x
+    assert out.to_tuple() == (x, []) and out.reg_loss is None
+    full = RoutedTransformerModelOutput(x, torch.ones(()), torch.ones(()), torch.ones(()), [x])
+    assert len(full.to_tuple()) == 5 and full[4] == [x]
+    vid = VideoPipelineOutput(frames=x)
+    assert vid.frames is x and vid.to_tuple() == (x,)
