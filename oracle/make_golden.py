@@ -78,6 +78,75 @@ def golden_coreset(ref):
     save("coreset.pt", out)
 
 
+FULLSIZE_CORESET_CASES = [
+    # (name, latent, coreset window, rate, heads, seed, heads per reference call)
+    ("wan13_480p_81f", (21, 30, 52), (3, 3, 2), 0.5, 12, 101, 4),       # BASELINE configs[0]/[1]
+    ("wan14_720p_81f", (21, 45, 80), (3, 3, 2), 0.5, 16, 102, 4),       # BASELINE configs[2] geometry, 16 of 40 heads
+    ("wan14_720p_77f_native", (20, 45, 80), (2, 3, 2), 0.5, 4, 103, 4),  # the reference's own training geometry
+    # spatially smooth activations (neighbouring tokens nearly parallel, cosines 0.99+): the regime where fp32 and
+    # fp64 rankings of the reference can differ; `smooth` = weight of the per-token noise on a shared direction
+    ("wan14_720p_81f_smooth", (21, 45, 80), (3, 3, 2), 0.5, 8, 104, 4, 0.02),
+]
+
+
+def fullsize_coreset_input(lat, heads, seed, smooth=None):
+    """The input of a full-size coreset case, regenerated from its seed by the tests ((1, H, S, 128) bf16)."""
+    S = lat[0] * lat[1] * lat[2]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((1, heads, S, D), generator=g)
+    if smooth is not None:
+        x = torch.randn((1, heads, 1, D), generator=g) + smooth * x
+    return x.to(torch.bfloat16)
+
+
+def golden_coreset_fullsize(ref):
+    """BASELINE-size index tables of the REFERENCE's pool_sequence_by_similarity (coreset_select.py:68-124), run in
+    fp32 (north_star's contract dtype) AND in fp64, on bf16-valued random inputs.  Stored: the fp64 tables (uint8)
+    and every (head, group) row where the fp32 run differs from the fp64 run, with the fp64 cosine gap between the
+    margins whose order flipped — the evidence for DESIGN.md section 3.3 (the kernel returns the fp64 ranking; the
+    fp32 reference may legitimately differ from it only where two similarities are closer than fp32 can resolve)."""
+    import torch.nn.functional as F
+    out = []
+    for name, lat, win, r, heads, seed, chunk, *rest in FULLSIZE_CORESET_CASES:
+        smooth = rest[0] if rest else None
+        info = ref.cs.get_group_info(lat, win, reduction_rate=r)
+        x = fullsize_coreset_input(lat, heads, seed, smooth)
+        tabs = {}
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            un, po = [], []
+            for h0 in range(0, heads, chunk):
+                _, m = ref.cs.pool_sequence_by_similarity(x[:, h0:h0 + chunk].to(dt), info)
+                un.append(m.unpooled_argsort_sim.to(torch.uint8))
+                po.append(m.pooled_argsort_sim.to(torch.uint8))
+            tabs[tag] = (torch.cat(un, dim=1), torch.cat(po, dim=1))
+        full32 = torch.cat(tabs["f32"], dim=-1)[0]          # (H, G, g-1): the complete ascending-similarity order
+        full64 = torch.cat(tabs["f64"], dim=-1)[0]
+        diff = (full32 != full64).any(dim=-1).nonzero()     # (n, 2): head, group
+        rows = []
+        for h, grp in diff.tolist():
+            c = x[0, h, info.center_indices[grp, 0]].double()
+            m = x[0, h, info.margin_indices[grp]].double()
+            sim = F.normalize(m, dim=-1) @ F.normalize(c, dim=-1)
+            a, b = full32[h, grp].long(), full64[h, grp].long()
+            pos = (a != b).nonzero().flatten()
+            # margins whose rank differs between the two runs; the largest fp64 gap among them bounds what fp32 lost
+            gap = (sim[a[pos]] - sim[b[pos]]).abs().max().item()
+            rows.append(dict(order_f32=full32[h, grp].clone(), gap_f64=gap))
+        n_groups = heads * full64.shape[1]
+        print(f"{name}: {len(rows)} of {n_groups} (head, group) rows differ between the reference in fp32 and fp64; "
+              f"largest fp64 gap {max([r_['gap_f64'] for r_ in rows], default=0.0):.2e}")
+        g1 = full64.shape[-1]
+        out.append(dict(name=name, latent=lat, window=win, rate=r, heads=heads, seed=seed, smooth=smooth,
+                        n_unpooled=info.num_unpooled_tokens_per_group,
+                        unpooled_f64=tabs["f64"][0], pooled_f64=tabs["f64"][1], n_groups=n_groups,
+                        # rows where the reference's fp32 run differs from its fp64 run: (head, group), the fp32
+                        # order of the g-1 margins, and the fp64 cosine gap between the margins that swapped
+                        f32_differs_at=diff.to(torch.int32),
+                        f32_order=torch.stack([r_["order_f32"] for r_ in rows]) if rows else torch.zeros((0, g1), dtype=torch.uint8),
+                        f32_gap=torch.tensor([r_["gap_f64"] for r_ in rows], dtype=torch.float64)))
+    save("coreset_fullsize.pt", out)
+
+
 def golden_tile_and_mask(ref):
     import torch.nn.attention.flex_attention as fa
     orig = ref.saf.create_block_mask
@@ -236,7 +305,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     which = set(sys.argv[1:])
     ref = ref_loader.load()
-    steps = [("group", golden_group_info), ("coreset", golden_coreset), ("mask", golden_tile_and_mask),
+    steps = [("group", golden_group_info), ("coreset", golden_coreset), ("coreset_full", golden_coreset_fullsize),
+             ("mask", golden_tile_and_mask),
              ("router", golden_router), ("wan", golden_wan_processor), ("hunyuan", golden_hunyuan_processor)]
     for name, fn in steps:
         if not which or name in which:

@@ -94,6 +94,39 @@ def test_selection_is_a_partition_at_full_size():
     assert torch.equal(un[:, :2].cpu(), un_ref) and torch.equal(po[:, :2].cpu(), po_ref)
 
 
+def test_fullsize_index_contract_vs_reference_fp32_and_fp64(golden, capsys):
+    """The index contract at the benchmarked geometries (Wan-1.3B 21x30x52, Wan-14B 21x45x80 and the reference's own
+    20x45x80), against tables produced by the REFERENCE's pool_sequence_by_similarity run in fp64 and in fp32
+    (tests/golden/coreset_fullsize.pt, oracle/make_golden.py):
+      * every row of the kernel's tables equals the reference-in-fp64 table;
+      * the rows where the kernel differs from the reference-in-fp32 are exactly the rows where the reference's own
+        fp32 and fp64 runs differ, and at each of them the fp64 cosine gap between the swapped margins is <= 4e-5
+        (what 127 fp32 additions can lose) — reported below, with counts."""
+    from oracle.make_golden import fullsize_coreset_input
+    report = []
+    for rec in golden("coreset_fullsize.pt"):
+        plan = ops.Plan(rec["latent"], (1, 1, 1), (1, 1, 1), rec["window"], rec["rate"])
+        assert plan.n_unpooled == rec["n_unpooled"]
+        x = fullsize_coreset_input(rec["latent"], rec["heads"], rec["seed"], rec["smooth"]).to(dev())
+        un, po = ops.coreset_select(plan, x)
+        un8, po8 = un.cpu().to(torch.uint8), po.cpu().to(torch.uint8)
+        assert torch.equal(un8, rec["unpooled_f64"]) and torch.equal(po8, rec["pooled_f64"]), rec["name"]
+        # reference-in-fp32 tables = fp64 tables with the recorded rows replaced
+        order32 = torch.cat([rec["unpooled_f64"], rec["pooled_f64"]], dim=-1)[0].clone()
+        at = rec["f32_differs_at"].long()
+        order32[at[:, 0], at[:, 1]] = rec["f32_order"]
+        mine = torch.cat([un8, po8], dim=-1)[0]
+        differs = (mine != order32).any(dim=-1).nonzero()
+        assert torch.equal(differs, at), rec["name"]
+        gaps = rec["f32_gap"]
+        assert gaps.numel() == 0 or gaps.max().item() <= 4e-5, rec["name"]
+        report.append(f"{rec['name']}: {rec['n_groups']} (head, group) rows == reference fp64; {at.shape[0]} differ "
+                      f"from reference fp32, largest fp64 cosine gap there "
+                      f"{(gaps.max().item() if gaps.numel() else 0.0):.2e}")
+    with capsys.disabled():
+        print("\n[coreset index contract] " + "\n[coreset index contract] ".join(report))
+
+
 def test_selection_near_ties_and_extreme_magnitudes_match_fp64_oracle():
     """The selection kernel ranks in fp32 and falls back to fp64 when two similarities are closer than the fp32 error
     bound or a norm leaves the range where the bound holds: near-duplicate margins (one bf16 ulp apart in one channel),
@@ -544,6 +577,55 @@ def test_full_size_properties_wan13():
     info = O.get_group_info(lat, lw, 0.5)
     ref = O.coreset_attention(qc[:, 1:2], kc[:, 1:2], vc[:, 1:2], info)
     assert_attn_close(out[:, 1:2], ref)
+
+
+def test_full_size_properties_wan14():
+    """The headline geometry (BASELINE configs[2]): Wan-14B 720p x 81 f, 21x45x80 = 75,600 tokens, tile (3,9,16) =
+    432 tokens (4 query tiles of 128 rows with a 48-row tail, 1296-key runs with a 16-key tail), no text; five heads
+    (two full, one coreset, two sliding) so both placements of a branch inside the merged launch are covered."""
+    lat, tile, win, lw, H = (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 5
+    plan = ops.Plan(lat, tile, win, lw, 0.5)
+    S = plan.seq_len
+    assert S == 75600 and plan.tile_tokens == 432 and plan.num_tiles == 175
+    g = torch.Generator().manual_seed(17)
+    q, k, v = (torch.randn((1, S, H, 128), generator=g).to(torch.bfloat16).to(dev()).transpose(1, 2) for _ in range(3))
+    branch = [0, 2, 1, 2, 0]
+    out = ops.routed_attention(plan, q, k, v, branch=branch)
+    assert torch.isfinite(out.float()).all()
+    # (1) softmax rows sum to one in every branch (V = 1 -> O = 1), which also proves every output row was written
+    o1 = ops.routed_attention(plan, q, k, torch.ones_like(v), branch=branch)
+    assert (o1.float() - 1).abs().max().item() <= 8e-3
+    # (2) one-hot blend == top-1 routing, exactly (three separate launches vs the merged one)
+    onehot = torch.nn.functional.one_hot(torch.tensor(branch), 3).float()[None]
+    assert torch.equal(ops.routed_attention(plan, q, k, v, weights=onehot), out)
+    # (3) heads are independent: the same head alone gives the same bits
+    for h in (1, 2, 4):
+        alone = ops.routed_attention(plan, q[:, h:h + 1], k[:, h:h + 1], v[:, h:h + 1], branch=[branch[h]])
+        assert torch.equal(alone, out[:, h:h + 1])
+    qc, kc, vc = q.float().cpu(), k.float().cpu(), v.float().cpu()
+    # (4) full heads: sampled rows against the fp32 oracle
+    rows = torch.arange(0, S, 601)
+    for h in (0, 4):
+        assert_attn_close(out[:, h:h + 1, rows], O.sdpa(qc[:, h:h + 1, rows], kc[:, h:h + 1], vc[:, h:h + 1]))
+    # (5) sliding heads: corner, edge and interior tiles (clamped windows) against the oracle on the window's keys
+    perm = O.tile_permutation(lat, tile).reshape(-1, plan.tile_tokens)
+    wins = O.tile_windows(lat, win, tile)
+    nt = [lat[d] // tile[d] for d in range(3)]
+    for h, tiles in ((1, (0, 4, 87, 174)), (3, (12, 90, 170))):
+        for t in tiles:
+            lo, hi = wins[t, :3], wins[t, 3:]
+            ids = [(a * nt[1] + b) * nt[2] + c for a in range(lo[0], hi[0] + 1) for b in range(lo[1], hi[1] + 1)
+                   for c in range(lo[2], hi[2] + 1)]
+            keys = perm[ids].reshape(-1)
+            assert keys.numel() == 27 * 432
+            ref = O.sdpa(qc[:, h:h + 1, perm[t]], kc[:, h:h + 1, keys], vc[:, h:h + 1, keys])
+            assert_attn_close(out[:, h:h + 1, perm[t]], ref)
+    # (6) the coreset head: selection tables equal the fp64 oracle, output equals the oracle on that selection
+    info = O.get_group_info(lat, lw, 0.5)
+    un, po = ops.coreset_select(plan, q[:, 2:3])
+    un_ref, po_ref = O.match(qc[:, 2:3].double(), info)
+    assert torch.equal(un.cpu(), un_ref) and torch.equal(po.cpu(), po_ref)
+    assert_attn_close(out[:, 2:3], O.coreset_attention(qc[:, 2:3], kc[:, 2:3], vc[:, 2:3], info))
 
 
 def test_full_size_properties_hunyuan_with_text():

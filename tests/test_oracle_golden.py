@@ -151,3 +151,20 @@ def test_ulysses_permutation_matches_reference(golden):
     back = O.ulysses_gather_heads(gathered)
     for r in range(P):
         assert torch.equal(back[r], shards[r])
+
+
+def test_oracle_matches_reference_fullsize_coreset_tables(golden):
+    """BASELINE-size index tables: the oracle run in fp64 equals the reference run in fp64 (first heads of every case
+    of tests/golden/coreset_fullsize.pt), and where the reference's own fp32 run differs from its fp64 run the fp64
+    cosine gap of the swapped margins is far below what fp32 accumulation can resolve."""
+    from oracle.make_golden import fullsize_coreset_input
+    for rec in golden("coreset_fullsize.pt"):
+        info = O.get_group_info(rec["latent"], rec["window"], rec["rate"])
+        assert info.num_unpooled_tokens_per_group == rec["n_unpooled"]
+        x = fullsize_coreset_input(rec["latent"], rec["heads"], rec["seed"], rec["smooth"])[:, :2]
+        un, po = O.match(x.double(), info)
+        assert torch.equal(un.to(torch.uint8), rec["unpooled_f64"][:, :2])
+        assert torch.equal(po.to(torch.uint8), rec["pooled_f64"][:, :2])
+        assert rec["f32_differs_at"].shape[0] == rec["f32_gap"].numel() == rec["f32_order"].shape[0]
+        if rec["f32_gap"].numel():
+            assert rec["f32_gap"].max().item() <= 4e-5          # kSimGap of vb_coreset_select_kernel
