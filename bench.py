@@ -2,7 +2,7 @@
 """bench.py — DiT denoise-step time of the VORTA-routed Wan 2.1 transformer on N B200s of one node.
 
     python bench.py --gpus N --steps K --warmup W            # N > 1: launched by torch.distributed.run, one rank per GPU
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the REFERENCE's own processor on the host CPU cores
 
 A "step" is one transformer forward (= one denoise step, no CFG doubling) over one synthetic latent video with
 random-init weights of the named architecture.  One JSON line is printed by rank 0 (see README / DESIGN.md section 6
@@ -11,6 +11,15 @@ for every field).  Workloads (BASELINE.json configs):
     wan13          : Wan2.1-T2V-1.3B, 480p x 81 f -> 21x30x52 = 32,760 tokens, 12 heads, 30 blocks [configs[1]]
 The default is the same for every N so that the driver's 1/2/4/8 scaling ratios compare like with like (12 heads
 do not divide by 8); the wan13 numbers are reported next to it at N = 1 in "aux".
+
+CPU legs.  The reference is pure PyTorch; its own files for the path travel to the GPU box under oracle/_ref
+(oracle/stage_ref.py).  What a CPU can actually execute in a bench run is BASELINE configs[0]: ONE Wan-1.3B routed
+self-attention layer (12 heads, 32,760 tokens) through the reference's WanAttnProcessorTripleEval
+(oracle/ref_layer.py).  `--impl reference` executes exactly that, once per step, on every host core — no
+extrapolation: its `value` is the measured time of its step, and `cpu_baseline.sample` says what share of the full
+workload one such step is.  The GPU arm runs the SAME layer on the same inputs through vorta_b200's processor of the
+same name (`like_for_like`, resident and with host buffers) next to the reference timed on the box's cores in the
+same run (`cpu_baseline`), and compares the two outputs.
 """
 from __future__ import annotations
 
@@ -27,18 +36,18 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "wan14": dict(model="wan2.1-t2v-14b", latent=(21, 45, 80), tile=(3, 9, 16), window=(3, 3, 3),
-                  lowres_window=(3, 3, 2), rate=0.5, text_tokens=512,
+                  lowres_window=(3, 3, 2), rate=0.5, text_tokens=512, heads=40, layers=40,
                   name="Wan2.1-T2V-14B 720p x81f (21x45x80 = 75,600 tokens, 40 heads, 40 blocks), one denoise step"),
     "wan13": dict(model="wan2.1-t2v-1.3b", latent=(21, 30, 52), tile=(3, 10, 4), window=(3, 3, 3),
-                  lowres_window=(3, 3, 2), rate=0.5, text_tokens=512,
+                  lowres_window=(3, 3, 2), rate=0.5, text_tokens=512, heads=12, layers=30,
                   name="Wan2.1-T2V-1.3B 480p x81f (21x30x52 = 32,760 tokens, 12 heads, 30 blocks), one denoise step"),
 }
 # contract test only (tests/test_bench_contract.py): tiny grid, 4 heads, 2 blocks; never a reported number
 WORKLOADS["tiny"] = dict(model="wan-contract-test", latent=(4, 6, 8), tile=(2, 3, 4), window=(3, 3, 3),
-                         lowres_window=(2, 3, 2), rate=0.5, text_tokens=16,
+                         lowres_window=(2, 3, 2), rate=0.5, text_tokens=16, heads=4, layers=2,
                          name="CONTRACT TEST ONLY: 2-block 4-head Wan shell, 4x6x8 = 192 tokens")
 WORKLOADS["hunyuan"] = dict(model="hunyuanvideo", latent=(33, 45, 80), tile=(3, 9, 16), window=(3, 3, 3),
-                            lowres_window=(3, 3, 2), rate=0.5, text_tokens=256, text_valid=64,
+                            lowres_window=(3, 3, 2), rate=0.5, text_tokens=256, text_valid=64, heads=24, layers=60,
                             name="HunyuanVideo 720p x129f (33x45x80 = 118,800 video tokens + 256 text (64 valid), 24 heads, "
                                  "20 dual + 40 single blocks), one denoise step")
 TAU_SPARSE = 0.3          # the reference's inference default (scripts/wan/inference.py:75)
@@ -55,16 +64,20 @@ def measured_peaks():
 
 
 def recorded_traffic(workload):
-    """DRAM bytes (read + write) per attention launch of this workload from the committed `ncu --set full` capture
-    (profiles/attn_traffic.json, written from the capture by profiles/summarize_full.py --traffic); None when no
-    capture of this workload has been committed."""
+    """DRAM bytes (read + write) per launch of the attention kernel for this workload, from the committed
+    `ncu --set full` captures (profiles/attn_traffic.json, written by profiles/summarize_full.py --traffic):
+    {"self": (bytes, source), "cross": (bytes, source)}; a key is absent when no capture has been committed."""
     path = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    out = {}
     try:
         with open(path) as f:
-            rec = json.load(f).get(workload)
-        return (float(rec["dram_bytes_per_launch"]), rec["source"]) if rec else (None, None)
-    except (OSError, ValueError, KeyError):
-        return None, None
+            rec = json.load(f).get(workload) or {}
+        for key in ("self", "cross"):
+            if key in rec:
+                out[key] = (float(rec[key]["dram_bytes_per_launch"]), rec[key]["source"])
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
+    return out
 
 
 class ClockSampler:
@@ -115,26 +128,95 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on the host cores, on a bounded sample of the workload
+# CPU legs: the REFERENCE's own processor (oracle/_ref or /root/reference) on the host cores, BASELINE configs[0]
 # ------------------------------------------------------------------------------------------------------------
-def cpu_sample_ms(wl, threads=None):
-    """One routed-attention layer sample: ONE head per branch at the workload's full sequence length, fp32, all
-    host threads.  Returns per-branch per-head milliseconds."""
-    import torch
-    from oracle import vorta_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
-    lat = wl["latent"]
-    S = lat[0] * lat[1] * lat[2]
-    g = torch.Generator().manual_seed(1234)
-    q, k, v = (torch.randn((1, 1, S, 128), generator=g).to(torch.bfloat16).float() for _ in range(3))
-    info = O.get_group_info(lat, wl["lowres_window"], wl["rate"])
-    out = {}
-    for e, name in ((0, "full"), (1, "coreset"), (2, "sliding")):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_cfg(wl):
+    from oracle import ref_layer as RL
+    return RL.TINY if wl is WORKLOADS["tiny"] else RL.CONFIG0
+
+
+def shared_config(wl, world):
+    """`config` of BOTH arms (the reference arm runs "on your arm's config"): the step workload, and the bounded
+    sample of it that the CPU legs execute."""
+    sample = cpu_sample_cfg(wl)
+    return dict(workload=wl["name"], tile=wl["tile"], window=wl["window"], coreset_window=wl["lowres_window"],
+                reduction_rate=wl["rate"], tau_sparse=TAU_SPARSE,
+                parallelism=f"ulysses{world}" if world > 1 else "single",
+                routing="random-init routers, top-1 per head",
+                l2="per-step working set (weights + activations) is far larger than the 126 MB L2; no flush needed",
+                cpu_sample=f"{sample['name']}; first third of the heads full, second coreset, last sliding tile; coreset "
+                           f"window {sample['lowres_window']}, tile {sample['tile']}, window {sample['window']}")
+
+
+def sample_share(wl):
+    """What part of the step workload's routed-attention FLOPs one configs[0] layer is (stated, never applied)."""
+    from oracle import ref_layer as RL
+    heads, layers = model_dims(wl)
+    S = wl["latent"][0] * wl["latent"][1] * wl["latent"][2]
+    # uniform 1/3 mix of the BASELINE.md section 3 per-head formulas, for orientation only
+    g = wl["lowres_window"][0] * wl["lowres_window"][1] * wl["lowres_window"][2]
+    s_c = (S // g) * int(g * (1 - wl["rate"]))
+    k_w = 27 * wl["tile"][0] * wl["tile"][1] * wl["tile"][2]
+    per_head = 4.0 * 128 * (S * S + s_c * s_c + S * k_w) / 3.0
+    return RL.algorithmic_flops(cpu_sample_cfg(wl))["attention"] / (per_head * heads * layers)
+
+
+def reference_leg(wl, n_timed, n_warm, threads=None, keep_output=False):
+    """Run the reference's WanAttnProcessorTripleEval on configs[0]: returns per-call ms list + bookkeeping."""
+    from oracle import ref_layer as RL
+    cores = threads or host_cores()
+    case = RL.build_case(cpu_sample_cfg(wl))
+    layer = RL.ReferenceLayer(case, threads=cores)
+    prep_s = layer.prepare()
+    t0 = time.perf_counter()
+    out = None
+    for _ in range(max(n_warm, 1)):              # the first call compiles flex_attention for the CPU
+        out = layer()
+    warm_s = time.perf_counter() - t0
+    ms = []
+    for _ in range(n_timed):
         t0 = time.perf_counter()
-        O.routed_attention(q, k, v, info, lat, wl["window"], wl["tile"], branch=torch.tensor([e]))
-        out[name] = (time.perf_counter() - t0) * 1e3
-    return out
+        out = layer()
+        ms.append((time.perf_counter() - t0) * 1e3)
+    return dict(ms=ms, cores=cores, prepare_s=prep_s, warm_s=warm_s, source=layer.source, case=case,
+                out=out if keep_output else None, flops=RL.algorithmic_flops(cpu_sample_cfg(wl)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                   # rank 0 alone runs the CPU arm; the other ranks exit 0
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # torchrun exports OMP_NUM_THREADS=1; must be set before torch loads
+    os.environ["MKL_NUM_THREADS"] = str(cores)
+    wl = WORKLOADS[args.workload]
+    r = reference_leg(wl, args.steps, args.warmup, threads=cores)
+    value = statistics.mean(r["ms"])
+    share = sample_share(wl)
+    sample = (f"each step = ONE real call of the reference's own WanAttnProcessorTripleEval "
+              f"(vorta/attention/wan.py:303-438, files from {'oracle/_ref' if r['source'] == 'staged' else '/root/reference'}) "
+              f"on BASELINE configs[0] (fp32 up-cast of the bf16 inputs, {cores} threads): "
+              f"{r['flops']['total'] / 1e12:.2f} TFLOP algorithmic = about 1/{1.0 / share:.0f} of the routed attention "
+              f"of one step of the workload; value is the measured time of that step, NOT scaled to the workload; "
+              f"untimed: block-mask build {r['prepare_s']:.0f} s + {max(args.warmup, 1)} warm-up calls {r['warm_s']:.0f} s")
+    line = dict(impl="reference", metric="dit_denoise_step_ms", value=value, unit="ms", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=value, higher_is_better=False, scaling="strong",
+                vs_baseline=None, dtype="f32", data="synthetic (storage-free hashed bf16-exact values)",
+                config=shared_config(wl, args.gpus),
+                cpu_baseline=dict(value=value, unit="ms", cores=cores, kind="reference", sample=sample,
+                                  ms_min=min(r["ms"]), ms_max=max(r["ms"]),
+                                  tflops=r["flops"]["total"] / (value * 1e-3) / 1e12),
+                like_for_like=dict(workload="BASELINE configs[0]", reference_cpu_ms=value),
+                e2e=dict(value=value, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
 
 
 def branch_counts(branches):
@@ -145,57 +227,9 @@ def branch_counts(branches):
     return c
 
 
-def cpu_step_ms(per_head_ms, counts):
-    return per_head_ms["full"] * counts[0] + per_head_ms["coreset"] * counts[1] + per_head_ms["sliding"] * counts[2]
-
-
 def model_dims(wl):
-    """(heads, attention layers) of the workload's architecture."""
-    if wl["model"] == "hunyuanvideo":
-        from vorta_b200.dit import HUNYUAN_CONFIGS
-        c = HUNYUAN_CONFIGS[wl["model"]]
-        return c.heads, c.num_layers + c.num_single_layers
-    from vorta_b200.dit import WAN_CONFIGS
-    c = WAN_CONFIGS[wl["model"]]
-    return c.heads, c.num_layers
-
-
-def run_reference(args):
-    import torch
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return                                   # rank 0 alone runs the CPU arm
-    heads, layers = model_dims(wl)
-    cores = torch.get_num_threads()
-    # the same head-branch mix the GPU arm reports is unknown here without a GPU: price a uniform 1/3 mix, which
-    # is what random-init routers produce in expectation; the GPU arm's line carries its exact counts
-    total_heads = heads * layers
-    counts = [total_heads / 3.0] * 3
-    for _ in range(args.warmup):
-        cpu_sample_ms(dict(wl, latent=(3, 9, 16), tile=(3, 9, 16), lowres_window=(3, 3, 2)))   # tiny warm-up
-    steps = []
-    last = None
-    for _ in range(args.steps):
-        last = cpu_sample_ms(wl)
-        steps.append(cpu_step_ms(last, counts))
-    value = statistics.mean(steps)
-    sample = (f"{args.steps} x (one head per branch: full / coreset / sliding at S={wl['latent'][0] * wl['latent'][1] * wl['latent'][2]}, "
-              f"fp32 torch CPU SDPA, oracle port of the reference path); step = per-head times x {heads} heads x "
-              f"{layers} layers at a uniform 1/3 branch mix; ATTENTION ONLY (the CPU linears are not timed)")
-    line = dict(impl="reference", metric="dit_denoise_step_ms", value=value, unit="ms", n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=value, higher_is_better=False, scaling="strong",
-                vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=wl["name"], tile=wl["tile"], window=wl["window"],
-                            coreset_window=wl["lowres_window"], reduction_rate=wl["rate"], tau_sparse=TAU_SPARSE,
-                            parallelism=f"host cpu, {cores} threads",
-                            routing="uniform 1/3 branch mix (expectation of random-init routers)",
-                            heads_per_branch_all_layers=dict(full=counts[0], coreset=counts[1], sliding=counts[2])),
-                cpu_baseline=dict(value=value, unit="ms", cores=cores, kind="port", sample=sample,
-                                  per_head_ms=last),
-                e2e=dict(value=value, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    """(heads, attention layers) of the workload's architecture (the reference arm must not import vorta_b200)."""
+    return wl["heads"], wl["layers"]
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -247,7 +281,7 @@ def make_step(model, wl, device, kw):
                                                return_dict=False, **extra)
 
 
-def time_steps(fn, steps, warmup, dist_on, profile=False):
+def time_steps(fn, steps, warmup, dist_on, profile=False, after_warmup=None):
     import torch
     import torch.distributed as dist
     for _ in range(warmup):
@@ -255,11 +289,15 @@ def time_steps(fn, steps, warmup, dist_on, profile=False):
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize()
+    if after_warmup is not None:
+        after_warmup()
     if profile:          # ncu --profile-from-start off: capture exactly one warmed-up step, outside the timing
         torch.cuda.cudart().cudaProfilerStart()
         fn()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
+        if after_warmup is not None:
+            after_warmup()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -309,18 +347,23 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
     counts = branch_counts(branches)
 
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    ops.stats_reset()
     ops.timing_enable(True)
-    ops.timing_collect()
+
+    def reset_counters():          # the timers and launch counters cover EXACTLY the timed steps
+        ops.timing_collect()
+        ops.stats_reset()
+
     sampler.start()
-    ms = time_steps(step_resident, args.steps, args.warmup, dist_on, profile=args.profile)
+    ms = time_steps(step_resident, args.steps, args.warmup, dist_on, profile=args.profile, after_warmup=reset_counters)
     clocks = sampler.stop()
     ops.timing_enable(False)
-    kernel_ms, kernel_launches, kernel_flops = ops.timing_collect()
-    # timing events were also recorded during warm-up: normalise per step over warmup + steps
-    n_all = args.steps + args.warmup + (1 if args.profile else 0)
-    attn_ms_step, attn_flops_step = kernel_ms / n_all, kernel_flops / n_all
-    launches_step = ops.stats()[0] / n_all
+    kinds = ops.timing_collect_kinds()
+    launches_step = ops.stats()[0] / args.steps
+    per = {}
+    for name, (k_ms, k_n, k_fl) in kinds.items():
+        per[name] = dict(ms_step=k_ms / args.steps, launches_step=k_n / args.steps, flops_step=k_fl / args.steps)
+    attn_ms_step = sum(v["ms_step"] for v in per.values())
+    attn_flops_step = sum(v["flops_step"] for v in per.values())
     e2e_ms = time_steps(step_e2e, args.steps, 1, dist_on) if with_e2e else None
     # whole-job attention flops: ranks hold disjoint head chunks
     if dist_on:
@@ -330,12 +373,131 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
         job_flops, attn_ms_max = float(fl[0].item()), float(mx[1].item())
     else:
         job_flops, attn_ms_max = attn_flops_step, attn_ms_step
+    # closed-form cross-check of the library's FLOP counter: head counts x BASELINE.md section 3 formulas (+ the dense
+    # cross-attention launches of the Wan blocks: 4 * S * text * 128 per head)
+    heads, layers = model_dims(wl)
+    S = wl["latent"][0] * wl["latent"][1] * wl["latent"][2]
+    plan_kw = dict(text_len=wl["text_tokens"], text_valid=wl.get("text_valid", 0)) if wl["model"] == "hunyuanvideo" else {}
+    plan = ops.Plan(wl["latent"], wl["tile"], wl["window"], wl["lowres_window"], wl["rate"], **plan_kw)
+    formula = sum(counts[e] * plan.flops_per_head(e) for e in range(3))
+    if wl["model"] != "hunyuanvideo":
+        formula += 4.0 * S * wl["text_tokens"] * 128 * heads * layers
     del model
     torch.cuda.empty_cache()
     return dict(ms=ms, e2e_ms=e2e_ms, clocks=clocks, counts=counts, attn_ms_step=attn_ms_step,
-                attn_flops_step=attn_flops_step, kernel_launches_step=kernel_launches / n_all,
-                launches_step=launches_step, job_flops=job_flops, attn_ms_max=attn_ms_max,
+                attn_flops_step=attn_flops_step, per_kind=per, launches_step=launches_step, job_flops=job_flops,
+                attn_ms_max=attn_ms_max, formula_flops_step=formula,
                 h2d=lat_h.numel() * 2 + txt_h.numel() * 2 + 4, d2h=out_h.numel() * 2, cfg=cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# like-for-like leg (N = 1): BASELINE configs[0] on the GPU through the reference-facing processor, next to the
+# reference's own processor on the host cores in the same run
+# ------------------------------------------------------------------------------------------------------------
+def like_for_like_leg(args, device, with_cpu=True):
+    import torch
+    from oracle import ref_layer as RL                  # input generator + the CPU checker / baseline of this leg
+    from vorta_b200.attention import WanAttnProcessorTripleEval, get_group_info
+    cfg = cpu_sample_cfg(WORKLOADS[args.workload])
+    case = RL.build_case(cfg)
+    attn = case["attn"].to(device, torch.bfloat16)
+    hs_h = case["hidden_states"].to(torch.bfloat16).pin_memory()
+    score_h = case["routing_score"].pin_memory()
+    rot = case["rotary_emb"].to(device)
+    hs_d = hs_h.to(device)
+    score_d = score_h.to(device)
+    out_h = torch.empty(hs_h.shape, dtype=torch.bfloat16).pin_memory()
+    proc = WanAttnProcessorTripleEval(check_input=True)
+    kw = dict(lowres_group_info=get_group_info(cfg["latent"], cfg["lowres_window"], cfg["rate"], device=device),
+              flex_attn_mask_func=None, window_size=cfg["window"], tile_size=cfg["tile"], latent_shape=cfg["latent"])
+
+    def resident():
+        return proc(attn, hs_d, None, None, rot, tau_sparse=cfg["tau_sparse"], routing_score=score_d, **kw)
+
+    def e2e():
+        a = hs_h.to(device, non_blocking=True)
+        b = score_h.to(device, non_blocking=True)
+        out = proc(attn, a, None, None, rot, tau_sparse=cfg["tau_sparse"], routing_score=b, **kw)
+        out_h.copy_(out, non_blocking=True)
+        return out
+
+    n = max(args.steps, 10)
+    ms = time_steps(resident, n, 3, False)
+    e2e_ms = time_steps(e2e, n, 3, False)
+    flops = RL.algorithmic_flops(cfg)
+    res = dict(workload=cfg["name"], gpu_ms=ms, gpu_e2e_ms=e2e_ms, calls=n,
+               h2d_bytes_per_call=hs_h.numel() * 2 + score_h.numel() * 4, d2h_bytes_per_call=out_h.numel() * 2,
+               gpu_tflops=flops["total"] / (ms * 1e-3) / 1e12,
+               api="vorta_b200.attention.WanAttnProcessorTripleEval.__call__ (the reference's processor signature)")
+    cpu = None
+    if with_cpu:
+        out_gpu = resident().float().cpu()
+        r = reference_leg(WORKLOADS[args.workload], 2, 1, keep_output=True)
+        ref = r["out"].float()
+        cos = torch.nn.functional.cosine_similarity(out_gpu.flatten(), ref.flatten(), dim=0).item()
+        err = (out_gpu - ref).abs().max().item()
+        cpu_ms = statistics.mean(r["ms"])
+        cpu = dict(value=cpu_ms, unit="ms", cores=r["cores"], kind="reference",
+                   sample=(f"the reference's own WanAttnProcessorTripleEval (vorta/attention/wan.py:303-438, files from "
+                           f"{'oracle/_ref' if r['source'] == 'staged' else '/root/reference'}) on BASELINE configs[0], fp32 up-cast of "
+                           f"the same bf16 inputs as like_for_like.gpu_ms, {r['cores']} threads, mean of 2 timed calls "
+                           f"after 1 warm-up; NOT scaled to the step workload (one such layer is about "
+                           f"1/{1.0 / sample_share(WORKLOADS[args.workload]):.0f} of its routed attention); untimed: block-mask "
+                           f"build {r['prepare_s']:.0f} s, warm-up {r['warm_s']:.0f} s"),
+                   ms_calls=r["ms"], tflops=flops["total"] / (cpu_ms * 1e-3) / 1e12)
+        res.update(reference_cpu_ms=cpu_ms, speedup_resident=cpu_ms / ms, speedup_e2e=cpu_ms / e2e_ms,
+                   parity=dict(cosine=cos, max_abs=err, ref_abs_max=ref.abs().max().item(),
+                               note="bf16 GPU layer (bf16 projections, RMSNorm, RoPE, attention) vs the fp32 reference "
+                                    "layer on identical inputs"))
+    return res, cpu
+
+
+# ------------------------------------------------------------------------------------------------------------
+# N > 1: the Ulysses path that is about to be timed == the single-GPU call, at the workload's real size
+# ------------------------------------------------------------------------------------------------------------
+def ulysses_parity(wl, device, world, rank):
+    """One routed self-attention layer at the workload's full geometry and head count: every rank holds the same
+    seeded q, k, v; the sequence-parallel path (token shards in, NVLink peer / NCCL exchange, this rank's heads,
+    exchange out, all-gather of the token shards) must reproduce rank 0's single-GPU vb_attn_fwd BIT FOR BIT
+    (reference semantics: vorta/ulysses/utils.py:15-124 around wan.py:243-294)."""
+    import torch
+    import torch.distributed as dist
+    from vorta_b200 import ops
+    from vorta_b200.attention.wan import WanAttnProcessorTripleEval
+    from vorta_b200.ulysses import SP_STATE, all_gather, peer
+    if wl["model"] == "hunyuanvideo":
+        return None
+    heads, _ = model_dims(wl)
+    plan = ops.Plan(wl["latent"], wl["tile"], wl["window"], wl["lowres_window"], wl["rate"])
+    S = plan.seq_len
+    s_loc = S // world
+    g = torch.Generator().manual_seed(4321)
+    branch = [(h * 7 + 1) % 3 for h in range(heads)]
+    q, k, v = (torch.randn((1, S, heads, 128), generator=g).to(torch.bfloat16).to(device).transpose(1, 2)
+               for _ in range(3))
+    proc = WanAttnProcessorTripleEval()
+    sl = slice(rank * s_loc, (rank + 1) * s_loc)
+    mine = proc._routed_attention(q[:, :, sl], k[:, :, sl], v[:, :, sl], plan, branch=branch)   # (1, H, S_loc, 128)
+    got = all_gather(mine.transpose(1, 2).contiguous(), dim=1)                                    # (1, S, H, 128)
+    res = None
+    if rank == 0:
+        en, sz = SP_STATE._enabled, SP_STATE._sp_size
+        SP_STATE._enabled, SP_STATE._sp_size = False, 1
+        try:
+            ref = ops.routed_attention(plan, q, k, v, branch=branch).transpose(1, 2)
+        finally:
+            SP_STATE._enabled, SP_STATE._sp_size = en, sz
+        err = (got.float() - ref.float()).abs().max().item()
+        res = dict(equal=bool(torch.equal(got, ref)), max_abs=err,
+                   what=f"one routed self-attention layer, {heads} heads x {S} tokens, branches (7h+1)%3, "
+                        f"{world}-rank Ulysses path vs rank 0's single-GPU call on the same q, k, v",
+                   exchange="nvlink-peer" if (os.environ.get("VB_ULYSSES", "peer") != "nccl"
+                                             and peer.disabled_reason() is None) else "nccl")
+    torch.cuda.synchronize()
+    dist.barrier()
+    del q, k, v, got, mine
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_gpu(args):
@@ -356,50 +518,71 @@ def run_gpu(args):
         from vorta_b200.ulysses import SP_STATE
         SP_STATE.setup_sp_group(world)
     wl = WORKLOADS[args.workload]
+    parity = ulysses_parity(wl, device, world, rank) if world > 1 else None
     r = run_workload(wl, args, rank, world, device)
     peaks = measured_peaks()
-    cfg = r["cfg"]
-    achieved = r["attn_flops_step"] / (r["attn_ms_step"] * 1e-3) / 1e12 if r["attn_ms_step"] > 0 else 0.0
-    traffic, traffic_source = recorded_traffic(args.workload)
+
+    def rate(flops, ms):
+        return flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+
+    routed, dense = r["per_kind"]["routed"], r["per_kind"]["dense"]
+    achieved = rate(routed["flops_step"], routed["ms_step"])       # the dominant kernel launch: a layer's routed self-attention
+    achieved_all = rate(r["attn_flops_step"], r["attn_ms_step"])
+    traffic = recorded_traffic(args.workload)
+    config = shared_config(wl, world)
     line = dict(
         metric="dit_denoise_step_ms", value=r["ms"], unit="ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=r["ms"], higher_is_better=False, scaling="strong", vs_baseline=None, dtype="bf16",
         data="synthetic (seeded N(0,1) latents / text embeddings, random-init weights)",
-        config=dict(workload=wl["name"], tile=wl["tile"], window=wl["window"], coreset_window=wl["lowres_window"],
-                    reduction_rate=wl["rate"], tau_sparse=TAU_SPARSE, parallelism=f"ulysses{world}" if world > 1 else "single",
-                    routing="random-init routers, top-1 per head", heads_per_branch_all_layers=dict(
-                        full=r["counts"][0], coreset=r["counts"][1], sliding=r["counts"][2]),
-                    l2="per-step working set (weights + activations) is far larger than the 126 MB L2; no flush needed"),
-        routed_attn_effective_tflops=r["job_flops"] / (r["attn_ms_max"] * 1e-3) / 1e12 if r["attn_ms_max"] > 0 else 0.0,
+        config=config,
+        routing_mix=dict(heads_per_branch_all_layers=dict(full=r["counts"][0], coreset=r["counts"][1],
+                                                          sliding=r["counts"][2])),
+        routed_attn_effective_tflops=rate(r["job_flops"], r["attn_ms_max"]),
         attn_kernel_ms_per_step=r["attn_ms_step"],
+        attn_flops_per_step=dict(library_counter=r["attn_flops_step"], closed_form=r["formula_flops_step"],
+                                 note="library counter = sum over the timed launches of this rank; closed form = head counts x "
+                                      "BASELINE.md section 3 formulas (+ 4*S*512*128 per head per block of dense cross attention)"
+                                      + (", whole job" if world > 1 else "")),
         roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
-                      frac=achieved / peaks["bf16"], traffic=traffic, traffic_unit="bytes / launch (DRAM read + write)",
-                      traffic_source=traffic_source, kernel="vb_attn_fwd_kernel",
+                      frac=achieved / peaks["bf16"], traffic=traffic.get("self", (None, None))[0],
+                      traffic_unit="bytes / launch (DRAM read + write)", traffic_source=traffic.get("self", (None, None))[1],
+                      kernel="vb_attn_fwd_kernel (routed self-attention launch: a layer's full + coreset + sliding heads in one grid)",
+                      ms_per_launch=routed["ms_step"] / max(routed["launches_step"], 1),
+                      launches_per_step=routed["launches_step"], ms_per_step=routed["ms_step"],
                       frac_of_burst=achieved / peaks["burst"], frac_of_spec_2250=achieved / 2250.0,
-                      launches_per_step=r["kernel_launches_step"], peak_source=peaks["source"]),
+                      peak_source=peaks["source"],
+                      cross_attention=dict(
+                          kernel="vb_attn_fwd_kernel (dense launch: 512 text keys per query)",
+                          achieved=rate(dense["flops_step"], dense["ms_step"]), unit="TFLOP/s",
+                          ms_per_launch=dense["ms_step"] / max(dense["launches_step"], 1),
+                          launches_per_step=dense["launches_step"], ms_per_step=dense["ms_step"],
+                          traffic=traffic.get("cross", (None, None))[0],
+                          hbm_gbs=(traffic["cross"][0] / (dense["ms_step"] / max(dense["launches_step"], 1) * 1e-3) / 1e9
+                                   if traffic.get("cross", (None, None))[0] and dense["ms_step"] > 0 else None),
+                          hbm_peak_gbs=peaks["hbm"]),
+                      all_attention_launches=dict(achieved=achieved_all, frac=achieved_all / peaks["bf16"])),
         clocks=r["clocks"],
         e2e=dict(value=r["e2e_ms"], unit="ms", h2d_bytes_per_step=r["h2d"], d2h_bytes_per_step=r["d2h"]),
         gpu_launches=int(round(r["launches_step"] * args.steps)),
     )
+    if parity is not None:
+        line["parity"] = parity
     if world == 1 and rank == 0:
-        # CPU baseline: the oracle port on the host cores, bounded sample (one head per branch)
         if not args.no_cpu_baseline:
-            per_head = cpu_sample_ms(wl)
-            S = wl["latent"][0] * wl["latent"][1] * wl["latent"][2]
-            line["cpu_baseline"] = dict(
-                value=cpu_step_ms(per_head, r["counts"]), unit="ms", cores=torch.get_num_threads(), kind="port",
-                per_head_ms=per_head,
-                sample=(f"one head per branch (full / coreset / sliding) at S={S}, fp32 torch CPU SDPA (oracle port of the "
-                        f"reference path), timed once; value = per-head ms x this run's head-branch counts over all "
-                        f"{model_dims(wl)[1]} layers; ATTENTION ONLY, the CPU linears are not timed"))
+            lfl, cpu = like_for_like_leg(args, device, with_cpu=True)
+            line["like_for_like"] = lfl
+            line["cpu_baseline"] = cpu
         if args.workload == "wan14" and not args.no_aux:
             a = run_workload(WORKLOADS["wan13"], args, rank, world, device, with_e2e=True)
-            ach = a["attn_flops_step"] / (a["attn_ms_step"] * 1e-3) / 1e12
+            ar = a["per_kind"]["routed"]
+            ach = rate(ar["flops_step"], ar["ms_step"])
             line["aux"] = dict(workload=WORKLOADS["wan13"]["name"], ms_per_step=a["ms"], e2e_ms=a["e2e_ms"],
                                heads_per_branch_all_layers=dict(full=a["counts"][0], coreset=a["counts"][1],
                                                                 sliding=a["counts"][2]),
-                               attn_kernel_ms_per_step=a["attn_ms_step"], attn_tflops=ach,
-                               roofline_frac=ach / peaks["bf16"])
+                               attn_kernel_ms_per_step=a["attn_ms_step"], routed_attn_tflops=ach,
+                               roofline_frac=ach / peaks["bf16"],
+                               cross_attn_tflops=rate(a["per_kind"]["dense"]["flops_step"],
+                                                      a["per_kind"]["dense"]["ms_step"]))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -221,6 +221,13 @@ int vb_block_rmsnorm_rope(const void* x, const void* weight, const float* cos_ta
  * returns the summed kernel time (ms), the number of launches and their algorithmic FLOPs, then clears. */
 void vb_timing_enable(int on);
 int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops);
+/* The same, split by caller: index VB_TIMING_ROUTED = launches made by vb_attn_fwd (the routed self-attention of a
+ * layer, all branches), VB_TIMING_DENSE = launches made by vb_attn_dense (cross attention, I2V image keys,
+ * use_original_attn).  Each array has VB_TIMING_KINDS entries. */
+#define VB_TIMING_ROUTED 0
+#define VB_TIMING_DENSE 1
+#define VB_TIMING_KINDS 2
+int vb_timing_collect_kinds(double* kernel_ms, int64_t* launches, double* flops);
 
 /* ------------------------------------------------------------------------------------------------------
  * Ulysses sequence parallelism helpers (vorta/ulysses/utils.py:15-93).  The exchange itself is an NCCL

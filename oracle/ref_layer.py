@@ -24,15 +24,22 @@ CONFIG0 = dict(heads=12, latent=(21, 30, 52), tile=(3, 10, 4), window=(3, 3, 3),
                name="configs[0]: one Wan2.1-T2V-1.3B routed self-attention layer (12 heads x 128, 21x30x52 = 32,760 "
                     "tokens; router scores -> top-1 -> q/k/v projections + RMSNorm + RoPE -> full / coreset / "
                     "sliding-tile attention -> output projection)")
-# fixed per-head routing of the like-for-like layer: heads 0-3 full, 4-7 coreset, 8-11 sliding tile
-BRANCH_OF_HEAD = [0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2]
+# tests/test_bench_contract.py only (bench.py --workload tiny): same code path on a 192-token, 3-head layer
+TINY = dict(heads=3, latent=(4, 6, 8), tile=(2, 3, 4), window=(3, 3, 3), lowres_window=(2, 3, 2), rate=0.5,
+            tau_sparse=0.3, name="CONTRACT TEST ONLY: one 3-head routed self-attention layer, 4x6x8 = 192 tokens")
+
+
+# fixed per-head routing of the like-for-like layer: heads 0-3 full, 4-7 coreset, 8-11 sliding tile (configs[0])
+def branch_of_head(heads: int):
+    """Thirds of the heads in head order: full, coreset, sliding tile."""
+    return [min(2, 3 * h // heads) for h in range(heads)]
 
 
 def routing_score(heads: int = 12) -> torch.Tensor:
-    """(1, H, 3) scores whose top-1 (above tau = 0.3) is BRANCH_OF_HEAD; bf16-exact values."""
+    """(1, H, 3) scores whose top-1 (above tau = 0.3) is branch_of_head; bf16-exact values."""
     s = torch.full((1, heads, 3), 0.125)
-    for h in range(heads):
-        s[0, h, BRANCH_OF_HEAD[h % len(BRANCH_OF_HEAD)]] = 0.75
+    for h, e in enumerate(branch_of_head(heads)):
+        s[0, h, e] = 0.75
     return s
 
 
@@ -58,7 +65,7 @@ def algorithmic_flops(cfg=CONFIG0) -> dict:
         k_w *= min(n // t, 2 * (w // 2) + 1)
     k_w *= cfg["tile"][0] * cfg["tile"][1] * cfg["tile"][2]
     per = [4.0 * S * S * D, 4.0 * S_c * S_c * D, 4.0 * D * S * k_w]
-    attn = sum(per[BRANCH_OF_HEAD[h % len(BRANCH_OF_HEAD)]] for h in range(H))
+    attn = sum(per[e] for e in branch_of_head(H))
     proj = 4 * 2.0 * S * (H * D) ** 2
     return dict(attention=attn, projections=proj, total=attn + proj)
 

@@ -27,18 +27,20 @@ KEYS = [
 
 
 def traffic(path, workload, source):
-    """--traffic: average DRAM bytes (read + write) per captured launch -> one JSON record for attn_traffic.json"""
+    """--traffic: DRAM bytes (read + write) of each captured launch -> JSON records for attn_traffic.json; launches
+    are labelled "self" (routed self-attention: the larger grid time) and "cross" (dense 512-key launch) by hand in
+    the committed file, here they are listed per launch with their grid sizes."""
     import json
     rows = list(csv.reader(open(path)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
-    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-        i = col[key]
-        tot += sum(float(r[i]) for r in data) * scale[units[i]]
-    print(json.dumps({workload: {"dram_bytes_per_launch": tot / len(data), "launches_captured": len(data),
-                                 "source": source}}))
+    out = []
+    for r in data:
+        tot = sum(float(r[col[key]]) * scale[units[col[key]]] for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        out.append({"grid": r[col["Grid Size"]] if "Grid Size" in col else None, "dram_bytes_per_launch": tot,
+                    "source": source})
+    print(json.dumps({workload: out}, indent=1))
 
 
 def main():

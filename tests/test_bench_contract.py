@@ -1,5 +1,5 @@
-"""bench.py output contract: the reference arm (CPU, oracle port) on the tiny contract-test workload must print ONE
-JSON line with every key the driver reads; the GPU arm is checked the same way on a B200."""
+"""bench.py output contract: the reference arm (the reference's own processor on the CPU) on the tiny contract-test
+workload must print ONE JSON line with every key the driver reads; the GPU arm is checked the same way on a B200."""
 import json
 import os
 import subprocess
@@ -27,7 +27,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["metric"] == "dit_denoise_step_ms" and d["unit"] == "ms" and d["higher_is_better"] is False
     assert d["vs_baseline"] is None and "workload" in d["config"] and "model" not in d["config"]
     assert d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"] == d["ms_per_step"]          # measured, never extrapolated
     assert d["e2e"] == {"value": d["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -46,5 +47,12 @@ def test_gpu_arm_prints_the_contract_line():
     assert d["gpu_launches"] > 0
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
+    lfl = d["like_for_like"]
+    assert lfl["gpu_ms"] > 0 and lfl["gpu_e2e_ms"] > 0 and lfl["reference_cpu_ms"] == d["cpu_baseline"]["value"]
+    assert lfl["parity"]["cosine"] >= 0.99
+    rr = d["roofline"]
+    assert rr["cross_attention"]["launches_per_step"] > 0 and rr["launches_per_step"] > 0
+    fl = d["attn_flops_per_step"]
+    assert abs(fl["library_counter"] - fl["closed_form"]) <= 1e-6 * fl["closed_form"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])

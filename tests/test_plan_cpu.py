@@ -201,3 +201,35 @@ def test_routed_output_container_behaves_like_base_output():
     assert len(full.to_tuple()) == 5 and full[4] == [x]
     vid = VideoPipelineOutput(frames=x)
     assert vid.frames is x and vid.to_tuple() == (x,)
+
+
+def test_router_checkpoint_roundtrip_with_reference_key_names(tmp_path):
+    """``router.pt`` of the reference (vorta/train/checkpoint.py:31-43 saves, :63-74 loads): the transformer's own
+    state-dict keys ``blocks.{i}.router.linear.{weight,bias}``.  Loading must set exactly the routers, leave every
+    other parameter alone and drop keys the model does not have (``k in full_state_dict``), e.g. a checkpoint trained
+    on a deeper model — not everything whose name merely contains "router"."""
+    from vorta_b200.dit import WanDiT
+    from vorta_b200.patch import apply_vorta_transformer, load_router_checkpoint
+    dev = torch.device("cpu")
+    model = apply_vorta_transformer(WanDiT.build("wan-contract-test", dev, torch.float32, seed=0))
+    n_blocks = len(model.blocks)
+    keys = [k for k in model.state_dict() if ".router." in k]
+    assert sorted(keys) == sorted(f"blocks.{i}.router.linear.{p}" for i in range(n_blocks) for p in ("weight", "bias"))
+    g = torch.Generator().manual_seed(3)
+    ckpt = {k: torch.randn(model.state_dict()[k].shape, generator=g) for k in keys}
+    ckpt[f"blocks.{n_blocks}.router.linear.weight"] = torch.zeros(3, 3)         # block the model does not have
+    ckpt["router_ema.decay"] = torch.tensor(0.5)                                 # contains "router", not a model key
+    path = tmp_path / "router.pt"
+    torch.save(ckpt, path)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    load_router_checkpoint(path, model)
+    after = model.state_dict()
+    for k in after:
+        if k in keys:
+            assert torch.equal(after[k], ckpt[k])
+        else:
+            assert torch.equal(after[k], before[k])
+    # a second model built through the install entry point with checkpoint_file= ends up with the same routers
+    model2 = apply_vorta_transformer(WanDiT.build("wan-contract-test", dev, torch.float32, seed=1), checkpoint_file=path)
+    for k in keys:
+        assert torch.equal(model2.state_dict()[k], ckpt[k])

@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "vb_attn_workspace_bytes", "vb_attn_fwd", "vb_attn_dense",
     "vb_block_ln_modulate", "vb_block_gate_residual", "vb_block_rmsnorm_rope",
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
+    "vb_timing_collect_kinds",
     "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_scatter_qkv", "vb_ulysses_unpack_heads",
 )
 
@@ -134,6 +135,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_timing_enable.argtypes = [C.c_int]
     lib.vb_timing_collect.restype = C.c_int
     lib.vb_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
+    lib.vb_timing_collect_kinds.restype = C.c_int
+    lib.vb_timing_collect_kinds.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     lib.vb_ulysses_pack_heads.restype = C.c_int
     lib.vb_ulysses_pack_heads.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, C.POINTER(i32), vp]
     lib.vb_ulysses_pack_qkv.restype = C.c_int

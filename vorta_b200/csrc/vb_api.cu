@@ -25,8 +25,13 @@ static thread_local int64_t g_launches = 0;
 static thread_local double g_flops = 0.0;
 // optional live timing of the attention kernel (bench.py roofline): event pairs on the launching stream
 static thread_local bool g_timing = false;
-static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
-static thread_local double g_timed_flops = 0.0;
+struct TimedLaunch {
+  cudaEvent_t ev0, ev1;
+  int kind;        // VB_TIMING_ROUTED (vb_attn_fwd) or VB_TIMING_DENSE (vb_attn_dense)
+  double flops;
+};
+static thread_local std::vector<TimedLaunch> g_events;
+static thread_local int g_launch_kind = VB_TIMING_ROUTED;
 
 // ---- kernels implemented in the other translation units -----------------------------------------
 int launch_coreset_select(const SelectParams& p, cudaStream_t stream);
@@ -581,8 +586,7 @@ static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_
   if (rc != VB_OK) return rc;
   if (g_timing) {
     VB_CUDA_OK(cudaEventRecord(ev1, stream));
-    g_events.push_back({ev0, ev1});
-    g_timed_flops += flops;
+    g_events.push_back({ev0, ev1, g_launch_kind, flops});
   }
   ++g_launches;
   g_flops += flops;
@@ -852,7 +856,10 @@ int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const 
   bl.sched = sched;
   std::vector<AttnHead> hs(heads);
   for (int h = 0; h < heads; ++h) hs[h] = AttnHead{h, h, 1.f, 0};
-  return run_branch(bl, a, hs, 0, batch, static_cast<cudaStream_t>(stream_));
+  g_launch_kind = VB_TIMING_DENSE;
+  const int rc = run_branch(bl, a, hs, 0, batch, static_cast<cudaStream_t>(stream_));
+  g_launch_kind = VB_TIMING_ROUTED;
+  return rc;
 }
 
 int vb_block_ln_modulate(const void* x, const float* weight, const float* bias, const float* scale, const float* shift,
@@ -883,21 +890,40 @@ int vb_block_rmsnorm_rope(const void* x, const void* weight, const float* cos_ta
 
 void vb_timing_enable(int on) { g_timing = on != 0; }
 
-int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops) {
-  double total = 0.0;
-  for (auto& e : g_events) {
-    VB_CUDA_OK(cudaEventSynchronize(e.second));
-    float ms = 0.f;
-    VB_CUDA_OK(cudaEventElapsedTime(&ms, e.first, e.second));
-    total += ms;
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
+int vb_timing_collect_kinds(double* kernel_ms, int64_t* launches, double* flops) {
+  for (int k = 0; k < VB_TIMING_KINDS; ++k) {
+    if (kernel_ms) kernel_ms[k] = 0.0;
+    if (launches) launches[k] = 0;
+    if (flops) flops[k] = 0.0;
   }
-  if (kernel_ms) *kernel_ms = total;
-  if (launches) *launches = static_cast<int64_t>(g_events.size());
-  if (flops) *flops = g_timed_flops;
+  for (auto& e : g_events) {
+    VB_CUDA_OK(cudaEventSynchronize(e.ev1));
+    float ms = 0.f;
+    VB_CUDA_OK(cudaEventElapsedTime(&ms, e.ev0, e.ev1));
+    const int k = e.kind >= 0 && e.kind < VB_TIMING_KINDS ? e.kind : 0;
+    if (kernel_ms) kernel_ms[k] += ms;
+    if (launches) launches[k] += 1;
+    if (flops) flops[k] += e.flops;
+    cudaEventDestroy(e.ev0);
+    cudaEventDestroy(e.ev1);
+  }
   g_events.clear();
-  g_timed_flops = 0.0;
+  return VB_OK;
+}
+
+int vb_timing_collect(double* kernel_ms, int64_t* launches, double* flops) {
+  double ms[VB_TIMING_KINDS], fl[VB_TIMING_KINDS];
+  int64_t n[VB_TIMING_KINDS];
+  const int rc = vb_timing_collect_kinds(ms, n, fl);
+  if (rc != VB_OK) return rc;
+  if (kernel_ms) *kernel_ms = 0.0;
+  if (launches) *launches = 0;
+  if (flops) *flops = 0.0;
+  for (int k = 0; k < VB_TIMING_KINDS; ++k) {
+    if (kernel_ms) *kernel_ms += ms[k];
+    if (launches) *launches += n[k];
+    if (flops) *flops += fl[k];
+  }
   return VB_OK;
 }
 

@@ -326,6 +326,14 @@ def timing_collect() -> Tuple[float, int, float]:
     return float(ms.value), int(n.value), float(fl.value)
 
 
+def timing_collect_kinds():
+    """Per caller: {"routed": (ms, launches, flops), "dense": (...)} — vb_attn_fwd launches (a layer's routed
+    self-attention, all branches in one grid) and vb_attn_dense launches (cross attention etc.) of the same kernel."""
+    ms, n, fl = (C.c_double * 2)(), (C.c_int64 * 2)(), (C.c_double * 2)()
+    L.check(L.lib().vb_timing_collect_kinds(ms, n, fl))
+    return {"routed": (float(ms[0]), int(n[0]), float(fl[0])), "dense": (float(ms[1]), int(n[1]), float(fl[1]))}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # fused elementwise kernels of the DiT block around the path (SURVEY.md section 8f rows 1-2)
 # ---------------------------------------------------------------------------------------------------------

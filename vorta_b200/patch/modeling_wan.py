@@ -152,10 +152,13 @@ def accumulate_loss(current_loss, new_loss):
 
 
 def load_router_checkpoint(checkpoint_file: os.PathLike, model) -> None:
-    """Router-only checkpoint (reference: vorta/train/checkpoint.py:63-74): keys ``blocks.{i}.router.linear.*``."""
+    """Router-only checkpoint ``router.pt`` (reference: vorta/train/checkpoint.py:63-74).  Keys are the transformer's
+    own state-dict names, ``blocks.{i}.router.linear.{weight,bias}`` (``transformer_blocks`` / ``single_transformer_blocks``
+    for HunyuanVideo); like the reference, entries whose key the model does not have are dropped silently and every
+    other parameter keeps its value."""
     state = torch.load(checkpoint_file, map_location="cpu", weights_only=True)
     own = model.state_dict()
-    own.update({k: v for k, v in state.items() if "router" in k})
+    own.update({k: v for k, v in state.items() if k in own})
     model.load_state_dict(own)
 
 
