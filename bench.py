@@ -434,7 +434,8 @@ def like_for_like_leg(args, device, with_cpu=True):
         out_gpu = resident().float().cpu()
         r = reference_leg(WORKLOADS[args.workload], 2, 1, keep_output=True)
         ref = r["out"].float()
-        cos = torch.nn.functional.cosine_similarity(out_gpu.flatten(), ref.flatten(), dim=0).item()
+        a64, b64 = out_gpu.flatten().double(), ref.flatten().double()
+        cos = float((a64 @ b64) / (a64.norm() * b64.norm()))
         err = (out_gpu - ref).abs().max().item()
         cpu_ms = statistics.mean(r["ms"])
         cpu = dict(value=cpu_ms, unit="ms", cores=r["cores"], kind="reference",
@@ -540,6 +541,7 @@ def run_gpu(args):
         routed_attn_effective_tflops=rate(r["job_flops"], r["attn_ms_max"]),
         attn_kernel_ms_per_step=r["attn_ms_step"],
         attn_flops_per_step=dict(library_counter=r["attn_flops_step"], closed_form=r["formula_flops_step"],
+                                 routed_launches=routed["flops_step"], dense_launches=dense["flops_step"],
                                  note="library counter = sum over the timed launches of this rank; closed form = head counts x "
                                       "BASELINE.md section 3 formulas (+ 4*S*512*128 per head per block of dense cross attention)"
                                       + (", whole job" if world > 1 else "")),

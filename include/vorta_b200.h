@@ -87,7 +87,11 @@ enum {
   VB_EXPORT_MARGIN_INDICES = 1, /* int64 (G, g-1)   == LowresGroupInfo.margin_indices */
   VB_EXPORT_TILE_MAP = 2,       /* int32 (S)  tile-major position -> raster token (tile.py:26-29) */
   VB_EXPORT_TILE_WINDOW = 3,    /* int32 (num_tiles, 6) lo/hi tile coordinate of each query tile's window */
-  VB_EXPORT_SLIDING_RUNS = 4    /* int32 (runs, 2) start/len in tile-major order */
+  VB_EXPORT_SLIDING_RUNS = 4,   /* int32 (runs, 2) start/len in tile-major order */
+  VB_EXPORT_SLIDING_ITEMS = 5   /* int32 (items, 12) work items of the sliding branch in launch order: q_row0[2],
+                                 * q_rows[2], run_begin, run_count, nq, n_blocks, split, run_begin2, run_count2, pad.
+                                 * An item is up to two 128-row query tiles; split = 1 pairs two single-tile leftovers
+                                 * of different tiles, tile 1 then attends to runs [run_begin2, run_begin2 + run_count2) */
 };
 /* Copies a host-side table for parity tests; *bytes is in: capacity, out: size. */
 int vb_plan_export(const vb_plan* plan, int what, void* dst, int64_t* bytes);
@@ -215,6 +219,17 @@ int vb_block_gate_residual(const void* x, const void* y, const float* gate, void
                            int32_t rows_per_batch, vb_stream_t stream);
 int vb_block_rmsnorm_rope(const void* x, const void* weight, const float* cos_tab, const float* sin_tab, void* out,
                           int64_t rows, int32_t dim, int32_t tokens_per_batch, float eps, vb_stream_t stream);
+
+/* HunyuanVideo Q / K prologue in one pass: per-head RMSNorm (weight bf16 (128), NULL = none) over every 128-channel
+ * head of x (batch, rows, heads*128) bf16 contiguous, then the rotation of channel pairs (2i, 2i+1) by
+ * (cos, sin)[row][i] (fp32 (rope_rows, 64), NULL = none) for rows < rope_rows (the video tokens; text rows are not
+ * rotated), written to rows [dst_row0, dst_row0 + rows) of out (batch, dst_rows, heads*128) — the joint
+ * [video | text] sequence the attention reads.  out may alias x when dst_rows == rows and dst_row0 == 0.
+ * replaces _step_qk_norm + _step_rotary_emb + the torch.cat of _step_encoder_to_qkv_and_concat
+ * (vorta/attention/hunyuan.py:62-134; diffusers' apply_rotary_emb(use_real=True, use_real_unbind_dim=-1)). */
+int vb_block_headnorm_rope(const void* x, const void* weight, const float* cos_tab, const float* sin_tab, void* out,
+                           int32_t batch, int32_t rows, int32_t heads, int32_t rope_rows, int32_t dst_rows,
+                           int32_t dst_row0, float eps, vb_stream_t stream);
 
 /* Live timing of the attention kernel for the roofline line of bench.py: while enabled, every launch of the
  * tcgen05 attention kernel is bracketed by CUDA events on its own stream; vb_timing_collect waits for them and

@@ -61,6 +61,22 @@ def main():
         check("wan cross attention", got, ref_cross)
     SP_STATE._enabled, SP_STATE._sp_size = False, 1        # single-GPU reference for the next case
 
+    # ---------------- Wan dense baseline (apply_sp_flashattn_transformer) under SP: whole DiT step ----------------
+    from vorta_b200.dit import WanDiT
+    from vorta_b200.dit import wan as wan_mod
+    from vorta_b200.patch import apply_sp_flashattn_transformer
+    wan_mod.WAN_CONFIGS["mgpu"] = wan_mod.WanConfig(dim=H * 128, heads=H, ffn_dim=256, num_layers=2, text_dim=64)
+    dense = apply_sp_flashattn_transformer(WanDiT.build("mgpu", dev, torch.bfloat16, seed=2))
+    lat_in = FX.det_tensor((1, 16, lat[0], 2 * lat[1], 2 * lat[2]), 20).to(dev, torch.bfloat16)
+    txt_in = FX.det_tensor((1, 12, 64), 21).to(dev, torch.bfloat16)
+    ts_in = torch.tensor([300.0], device=dev)
+    with torch.no_grad():
+        ref_dense = dense(lat_in, ts_in, txt_in, return_dict=False)[0]
+        SP_STATE._enabled, SP_STATE._sp_size = True, world
+        got_dense = dense(lat_in, ts_in, txt_in, return_dict=False)[0]
+        check("wan dense baseline DiT step (sp flashattn)", got_dense, ref_dense)
+    SP_STATE._enabled, SP_STATE._sp_size = False, 1
+
     # ---------------- HunyuanVideo single-stream block with a padded text tail ----------------
     lat, tile, win, lw, TL, TV = (2, 8, 8), (1, 4, 4), (3, 3, 3), (2, 2, 2), 16, 11
     S = 128

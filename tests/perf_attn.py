@@ -29,12 +29,17 @@ def main():
     tag = os.environ.get("VB_TAG", "default")
     cases = [("dense S=16384 H=37 (16 full waves)", (1, 1, 16384), (1, 1, 16384), (1, 1, 1), (1, 1, 2), 37, 0),
              ("dense S=32768 H=37", (1, 1, 32768), (1, 1, 32768), (1, 1, 1), (1, 1, 2), 37, 0)]
-    if not os.environ.get("VB_QUICK"):
+    if os.environ.get("VB_QUICK2"):
+        cases = [("wan14 native sliding (5,9,8) H=16", (20, 45, 80), (5, 9, 8), (3, 3, 3), (2, 3, 2), 16, 2),
+                 ("wan13 grid sliding (3,10,4) H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 2)]
+    elif not os.environ.get("VB_QUICK"):
         cases += [("wan14 grid full H=8", (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 8, 0),
                   ("wan14 grid coreset H=16", (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 16, 1),
                   ("wan14 grid sliding H=16", (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 16, 2),
                   ("wan14 native sliding (5,9,8) H=16", (20, 45, 80), (5, 9, 8), (3, 3, 3), (2, 3, 2), 16, 2),
-                  ("wan13 grid sliding (3,10,4) H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 2)]
+                  ("wan13 grid sliding (3,10,4) H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 2),
+                  ("wan13 grid coreset H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 1),
+                  ("wan13 grid full H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 0)]
     for name, lat, tile, win, lw, H, e in cases:
         plan = ops.Plan(lat, tile, win, lw, 0.5)
         S = plan.seq_len
@@ -46,5 +51,27 @@ def main():
         torch.cuda.empty_cache()
 
 
+def cross():
+    """Wan-14B cross attention: 40 heads x 75,600 queries x 512 text keys (vb_attn_dense)."""
+    tag = os.environ.get("VB_TAG", "default")
+    q = torch.randn((1, 75600, 40, 128), device="cuda").bfloat16().transpose(1, 2)
+    k, v = (torch.randn((1, 512, 40, 128), device="cuda").bfloat16().transpose(1, 2) for _ in range(2))
+    for _ in range(3):
+        ops.attn_dense(q, k, v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(10):
+        ops.attn_dense(q, k, v)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = 4.0 * 75600 * 512 * 128 * 40
+    gb = (2 * 75600 * 40 * 128 * 2 + 2 * 512 * 40 * 128 * 2) / 1e9
+    print(f"[{tag}] wan14 cross attention 40 heads x 75600 x 512   {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
+          f"{gb / ms * 1e3:8.1f} GB/s of algorithmic Q+O+K+V bytes", flush=True)
+
+
 if __name__ == "__main__":
+    cross()
     main()

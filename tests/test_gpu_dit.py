@@ -240,3 +240,33 @@ def test_wan_forward_reference_return_structure_and_losses():
     # training through the blend is refused loudly (no attention backward yet)
     with pytest.raises(NotImplementedError):
         model(x, ts, text, self_attention_kwargs=kw)
+
+
+def test_wan_dense_baseline_forward_equals_all_full_routing():
+    """apply_sp_flashattn_transformer (modeling_wan.py:313-323): the un-routed baseline runs through the same
+    token-sharded forward with the base processors; it must equal the routed model when every head is routed to the full
+    branch (same kernel, same q / k / v), and refuse router outputs."""
+    from vorta_b200.patch import apply_sp_flashattn_transformer
+    wan_mod.WAN_CONFIGS["tiny"] = wan_mod.WanConfig(dim=384, heads=3, ffn_dim=512, num_layers=2, text_dim=64)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(6)
+    latents = torch.randn((1, 16, LAT[0], 2 * LAT[1], 2 * LAT[2]), generator=g).to(dev, torch.bfloat16)
+    text = torch.randn((1, 20, 64), generator=g).to(dev, torch.bfloat16)
+    ts = torch.tensor([431.0], device=dev)
+    routed = WanDiT.build("tiny", dev, torch.bfloat16, seed=8)
+    apply_vorta_transformer(routed, router_dtype=torch.float32)
+    with torch.no_grad():
+        for blk in routed.blocks:
+            blk.router.linear.weight.zero_()
+            blk.router.linear.bias.copy_(torch.tensor([4., 0., 0.]).repeat(3))      # every head -> full attention
+    kw = prepare_wan_self_attn_kwargs(dict(latent_shape=LAT, window_size=WIN, tile_size=TILE, lowres_window_size=LW,
+                                           lowres_reduction_rate=0.5), dev, tau_sparse=0.3)
+    with torch.no_grad():
+        want = routed(latents, ts, text, self_attention_kwargs=kw, return_dict=False)[0]
+    dense = WanDiT.build("tiny", dev, torch.bfloat16, seed=8)
+    apply_sp_flashattn_transformer(dense)
+    with torch.no_grad():
+        got = dense(latents, ts, text, return_dict=False)[0]
+        assert torch.equal(got, want)
+        with pytest.raises(ValueError):
+            dense(latents, ts, text, return_routing_scores=True)

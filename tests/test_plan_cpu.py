@@ -233,3 +233,72 @@ def test_router_checkpoint_roundtrip_with_reference_key_names(tmp_path):
     model2 = apply_vorta_transformer(WanDiT.build("wan-contract-test", dev, torch.float32, seed=1), checkpoint_file=path)
     for k in keys:
         assert torch.equal(model2.state_dict()[k], ckpt[k])
+
+
+@pytest.mark.parametrize("lat,tile,win,tl,tv", [
+    ((21, 30, 52), (3, 10, 4), (3, 3, 3), 0, 0),      # Wan-1.3B: 120-token tiles -> every item is a split pair
+    ((21, 45, 80), (3, 9, 16), (3, 3, 3), 0, 0),      # Wan-14B: 432-token tiles -> two shared-run items per tile
+    ((20, 45, 80), (5, 9, 8), (3, 3, 3), 0, 0),       # reference-native: 360 = 256 + 104 -> one shared + one single item
+    ((4, 8, 8), (2, 4, 4), (3, 3, 3), 16, 11),        # text segment: text queries are their own items
+    ((6, 6, 8), (1, 3, 4), (3, 1, 3), 0, 0),          # tiny tiles (12 tokens), odd tile count
+])
+def test_sliding_work_items_cover_every_query_once_with_its_window(lat, tile, win, tl, tv):
+    """The work items of the persistent attention kernel (vb_attn.cu): every query row of the tile-major sequence is in
+    exactly one 128-row slot; the run list of its slot is the window of its tile (bit-exact against the oracle's dense
+    mask); items that pair two different tiles ("split") walk the same number of key blocks; items are ordered longest
+    first."""
+    plan = ops.Plan(lat, tile, win, (1, 1, 1), 0.5, text_len=tl, text_valid=tv, n_unpooled=0)
+    items = plan.export(L.EXPORT_SLIDING_ITEMS).reshape(-1, 12)
+    runs = plan.export(L.EXPORT_SLIDING_RUNS).reshape(-1, 2)
+    S, tau = plan.seq_len, plan.tile_tokens
+    nt = [lat[d] // tile[d] for d in range(3)]
+    wins = O.tile_windows(lat, win, tile)
+    dense = O.sliding_tile_mask(lat, win, tile, tl, tv) if S <= 4096 else None     # tile-major index space
+
+    def merged(intervals):
+        out = []
+        for a, b in sorted(intervals):
+            if out and out[-1][1] == a:
+                out[-1][1] = b
+            else:
+                out.append([a, b])
+        return out
+
+    def expected_keys(row):
+        if row >= S:                                   # a valid text query sees every non-pad key
+            return [[0, S + tv]]
+        lo, hi = wins[row // tau, :3], wins[row // tau, 3:]
+        iv = [(((x * nt[1] + y) * nt[2] + lo[2]) * tau, ((x * nt[1] + y) * nt[2] + hi[2] + 1) * tau)
+              for x in range(lo[0], hi[0] + 1) for y in range(lo[1], hi[1] + 1)]
+        if tv:
+            iv.append((S, S + tv))
+        return merged(iv)
+
+    seen = np.zeros(S + tv, dtype=np.int32)
+    cost = []
+    for q0a, q0b, qra, qrb, rb, rc, nq, nblk, split, rb2, rc2, _ in items.tolist():
+        assert nq in (1, 2) and split in (0, 1) and (split == 0 or nq == 2)
+        slots = [(q0a, qra, rb, rc)]
+        if nq == 2:
+            slots.append((q0b, qrb, rb2, rc2) if split else (q0b, qrb, rb, rc))
+        for q0, qr, b, c in slots:
+            assert 0 < qr <= 128
+            seen[q0:q0 + qr] += 1
+            mine = [(st, st + ln) for st, ln in runs[b:b + c].tolist()]
+            assert sum((e - st + 127) // 128 for st, e in mine) == nblk
+            for r in (q0, q0 + qr - 1):                # first and last row of the slot share the slot's run list
+                assert merged(mine) == expected_keys(r), (q0, qr, r)
+                if dense is not None:
+                    keys = torch.zeros(S + tl, dtype=torch.bool)
+                    for st, e in mine:
+                        keys[st:e] = True
+                    assert torch.equal(keys, dense[r])
+        cost.append(nblk * nq)
+    assert (seen == 1).all()
+    assert cost == sorted(cost, reverse=True)
+    n_single = sum(1 for it in items.tolist() if it[6] == 1)
+    n_split = sum(1 for it in items.tolist() if it[8] == 1)
+    if tau <= 128:                      # single-tile branch: leftovers are paired (at most one odd item per block count)
+        assert n_split > 0 and n_single <= 2
+    else:                               # mixed with natural two-tile items: leftovers stay single
+        assert n_split == 0

@@ -27,7 +27,8 @@ ATTN_CORESET_KV_FROM_K = 1
 (PLAN_SEQ_LEN, PLAN_NUM_GROUPS, PLAN_GROUP_SIZE, PLAN_CORESET_LEN, PLAN_NUM_TILES, PLAN_TILE_TOKENS,
  PLAN_NUM_POOLED, PLAN_KEYS_PER_QUERY, PLAN_SLIDING_PAIRS, PLAN_SLIDING_RUNS) = range(10)
 # vb_plan_export keys
-EXPORT_CENTER_INDICES, EXPORT_MARGIN_INDICES, EXPORT_TILE_MAP, EXPORT_TILE_WINDOW, EXPORT_SLIDING_RUNS = range(5)
+(EXPORT_CENTER_INDICES, EXPORT_MARGIN_INDICES, EXPORT_TILE_MAP, EXPORT_TILE_WINDOW, EXPORT_SLIDING_RUNS,
+ EXPORT_SLIDING_ITEMS) = range(6)
 
 # every symbol include/vorta_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
@@ -35,7 +36,7 @@ EXPORTED_SYMBOLS = (
     "vb_plan_create", "vb_plan_destroy", "vb_plan_set_text_valid", "vb_plan_query", "vb_plan_export",
     "vb_router_forward", "vb_coreset_select", "vb_coreset_tables", "vb_gather_rows",
     "vb_attn_workspace_bytes", "vb_attn_fwd", "vb_attn_dense",
-    "vb_block_ln_modulate", "vb_block_gate_residual", "vb_block_rmsnorm_rope",
+    "vb_block_ln_modulate", "vb_block_gate_residual", "vb_block_rmsnorm_rope", "vb_block_headnorm_rope",
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
     "vb_timing_collect_kinds",
     "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_scatter_qkv", "vb_ulysses_unpack_heads",
@@ -131,6 +132,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_block_gate_residual.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.vb_block_rmsnorm_rope.restype = C.c_int
     lib.vb_block_rmsnorm_rope.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, f32, vp]
+    lib.vb_block_headnorm_rope.restype = C.c_int
+    lib.vb_block_headnorm_rope.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.vb_timing_enable.restype = None
     lib.vb_timing_enable.argtypes = [C.c_int]
     lib.vb_timing_collect.restype = C.c_int

@@ -31,6 +31,43 @@ def apply_rotary_emb(x: torch.Tensor, freqs_cis: Tuple[torch.Tensor, torch.Tenso
     return (x.float() * cos + x_rot.float() * sin).to(x.dtype)
 
 
+_ROPE_CACHE = {}
+
+
+def _rope_tables(image_rotary_emb):
+    """fp32 (S_loc, 64) cos / sin tables for the prologue kernel from diffusers' pair-repeated (S, 128) tables
+    (cos[:, 2i] == cos[:, 2i + 1]); the same tuple is handed to every block of a forward, so the last one is cached."""
+    cos, sin = image_rotary_emb
+    key = (cos.data_ptr(), sin.data_ptr(), tuple(cos.shape), SP_STATE.group_local_rank if SP_STATE.enabled else -1)
+    hit = _ROPE_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    c = shrink_dim(cos, dim=0)[:, 0::2].float().contiguous()
+    s = shrink_dim(sin, dim=0)[:, 0::2].float().contiguous()
+    _ROPE_CACHE["last"] = (key, c, s, cos, sin)             # keep the sources alive so the pointers stay unique
+    return c, s
+
+
+def _head_norm(norm):
+    """(weight, eps) of a per-head RMSNorm module the prologue kernel can apply, (None, 0) for no norm, or False when
+    the module is something else (then the eager steps run)."""
+    if norm is None:
+        return None, 0.0
+    w = getattr(norm, "weight", None)
+    if w is None or w.numel() != 128 or getattr(norm, "bias", None) is not None:
+        return False
+    eps = getattr(norm, "eps", None)
+    return w, float(eps) if eps is not None else float(torch.finfo(torch.bfloat16).eps)
+
+
+def _linear_into(linear, x2d: torch.Tensor, out2d: torch.Tensor) -> None:
+    """out2d = linear(x2d), written in place by the GEMM (no copy into the joint sequence afterwards)."""
+    if linear.bias is not None:
+        torch.addmm(linear.bias, x2d, linear.weight.t(), out=out2d)
+    else:
+        torch.mm(x2d, linear.weight.t(), out=out2d)
+
+
 def _valid_text(attention_mask: torch.Tensor, video_len: int) -> int:
     """Number of un-padded text tokens from the boolean mask (B, 1, 1, S + S_text) (hunyuan.py:169)."""
     return int(attention_mask.reshape(-1).sum().item()) - video_len
@@ -140,7 +177,45 @@ class HunyuanVideoFlashAttnProcessor:
             encoder_hidden_states = attn.to_add_out(encoder_hidden_states)
         return hidden_states, encoder_hidden_states
 
+    def _qkv_fused(self, attn, hidden_states, encoder_hidden_states, image_rotary_emb):
+        """Steps 1-4 (hunyuan.py:42-134) with ONE elementwise pass per Q / K stream: the projection GEMMs write
+        (B, rows, H*128); ``vb_block_headnorm_rope`` applies the per-head RMSNorm, rotates the video rows and places
+        the rows in the joint [video | text] tensor; V is written into it by the GEMM itself.  None = not applicable
+        (other norm modules, dtypes, devices): the eager steps run instead."""
+        norms = [_head_norm(getattr(attn, n, None)) for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k")]
+        if (hidden_states.dtype != torch.bfloat16 or not hidden_states.is_cuda or hidden_states.dim() != 3
+                or any(n is False for n in norms) or torch.is_grad_enabled() and hidden_states.requires_grad):
+            return None
+        (wq, eq_), (wk, ek_), (waq, eaq), (wak, eak) = norms
+        B, S, _ = hidden_states.shape
+        T = encoder_hidden_states.shape[1]
+        H = attn.heads
+        cos, sin = _rope_tables(image_rotary_emb)
+        hidden_states = hidden_states.contiguous()
+        encoder_hidden_states = encoder_hidden_states.contiguous()
+        if attn.add_q_proj is None:
+            # single-stream block: one projection over the joint sequence, norm everywhere, RoPE on the video rows
+            joint = torch.cat([hidden_states, encoder_hidden_states], dim=1)
+            query = ops.headnorm_rope(attn.to_q(joint), wq, eq_, H, cos, sin, rope_rows=S)
+            key = ops.headnorm_rope(attn.to_k(joint), wk, ek_, H, cos, sin, rope_rows=S)
+            value = attn.to_v(joint)
+        else:
+            dim = H * 128
+            query = torch.empty((B, S + T, dim), dtype=hidden_states.dtype, device=hidden_states.device)
+            key, value = torch.empty_like(query), torch.empty_like(query)
+            ops.headnorm_rope(attn.to_q(hidden_states), wq, eq_, H, cos, sin, out=query)
+            ops.headnorm_rope(attn.to_k(hidden_states), wk, ek_, H, cos, sin, out=key)
+            ops.headnorm_rope(attn.add_q_proj(encoder_hidden_states), waq, eaq, H, out=query, dst_row0=S)
+            ops.headnorm_rope(attn.add_k_proj(encoder_hidden_states), wak, eak, H, out=key, dst_row0=S)
+            for b in range(B):
+                _linear_into(attn.to_v, hidden_states[b], value[b, :S])
+                _linear_into(attn.add_v_proj, encoder_hidden_states[b], value[b, S:])
+        return tuple(t.unflatten(2, (H, -1)).transpose(1, 2) for t in (query, key, value))
+
     def _qkv(self, attn, hidden_states, encoder_hidden_states, image_rotary_emb):
+        fused = self._qkv_fused(attn, hidden_states, encoder_hidden_states, image_rotary_emb)
+        if fused is not None:
+            return fused
         query, key, value = self._step_to_qkv_and_unflatten(attn, hidden_states, encoder_hidden_states)
         query, key = self._step_qk_norm(attn, query, key)
         query, key = self._step_rotary_emb(attn, query, key, encoder_hidden_states.shape[1], image_rotary_emb)

@@ -7,9 +7,17 @@
 #include <algorithm>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges cost a few ns unless a profiler is attached
+
 #include "vb_common.cuh"
 
 namespace vb {
+
+// NVTX range over one host-side phase of the path (visible in nsys / ncu --nvtx)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---- error plumbing -----------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -54,6 +62,9 @@ int launch_gate_residual(const void* x, const void* y, const float* gate, void* 
                          int rows_per_batch, cudaStream_t stream);
 int launch_rmsnorm_rope(const void* x, const void* weight, const float* cs, const float* sn, void* out, int64_t rows,
                         int dim, int tokens_per_batch, float eps, cudaStream_t stream);
+int launch_headnorm_rope(const void* x, const void* weight, const float* cs, const float* sn, void* out, int batch,
+                         int rows, int heads, int rope_rows, int dst_rows, int dst_row0, float eps,
+                         cudaStream_t stream);
 int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                                const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int heads,
                                int world, int rank, const int32_t* head_at, cudaStream_t stream);
@@ -71,12 +82,15 @@ struct Schedule {
   double flops_per_head = 0.0;   // 4 * D * sum_q keys(q)
 
   void add_query_range(int row0, int n_rows, int run_begin, int run_count, int64_t keys) {
-    // split [row0, row0+n_rows) into 128-row tiles, two per CTA
+    // split [row0, row0+n_rows) into 128-row tiles, two per work item
+    int n_blocks = 0;
+    for (int r = 0; r < run_count; ++r) n_blocks += (runs[run_begin + r].len + kBlockN - 1) / kBlockN;
     for (int off = 0; off < n_rows; off += 2 * kBlockM) {
       QPair qp;
       memset(&qp, 0, sizeof(qp));
       qp.run_begin = run_begin;
       qp.run_count = run_count;
+      qp.n_blocks = n_blocks;
       qp.q_row0[0] = row0 + off;
       qp.q_rows[0] = std::min(kBlockM, n_rows - off);
       qp.nq = 1;
@@ -88,6 +102,50 @@ struct Schedule {
       pairs.push_back(qp);
     }
     flops_per_head += 4.0 * kHeadDim * static_cast<double>(n_rows) * static_cast<double>(keys);
+  }
+  // Single-tile items leave one of the CTA's two tile pipelines idle.  When EVERY item of the branch is a single tile
+  // (sliding tiles of <= 128 tokens, e.g. the 120-token tiles of Wan-1.3B), pair two of them that walk the same number
+  // of key blocks into ONE split item: tile 1 keeps its own run list (measured 724 -> 768 TFLOP/s, profiles/r2b_*).
+  // A split item stages every K/V block for one tile only, i.e. twice the ring traffic per MMA; mixed with ordinary
+  // two-tile items (the 104-row leftover of a 360-token tile) that cost more than the idle pipeline it fills
+  // (1140 -> 986 TFLOP/s), so those leftovers stay single.  Then order the items longest first (stable): the
+  // persistent kernel hands them out greedily.
+  void finalize() {
+    bool all_single = !pairs.empty();
+    for (const QPair& qp : pairs) all_single = all_single && qp.nq == 1;
+    if (all_single && getenv("VB_ATTN_NO_SPLIT") == nullptr) {
+      std::vector<QPair> out;
+      std::vector<int> open_by_blocks;        // index in `out` of an unpaired single-tile item, per block count
+      for (const QPair& qp : pairs) {
+        if (qp.nq != 1) {
+          out.push_back(qp);
+          continue;
+        }
+        int partner = -1;
+        for (size_t i = 0; i < open_by_blocks.size(); ++i)
+          if (out[open_by_blocks[i]].n_blocks == qp.n_blocks) {
+            partner = static_cast<int>(i);
+            break;
+          }
+        if (partner < 0) {
+          open_by_blocks.push_back(static_cast<int>(out.size()));
+          out.push_back(qp);
+        } else {
+          QPair& a = out[open_by_blocks[partner]];
+          a.q_row0[1] = qp.q_row0[0];
+          a.q_rows[1] = qp.q_rows[0];
+          a.nq = 2;
+          a.split = (qp.run_begin == a.run_begin && qp.run_count == a.run_count) ? 0 : 1;
+          a.run_begin2 = qp.run_begin;
+          a.run_count2 = qp.run_count;
+          open_by_blocks.erase(open_by_blocks.begin() + partner);
+        }
+      }
+      pairs.swap(out);
+    }
+    std::stable_sort(pairs.begin(), pairs.end(), [](const QPair& a, const QPair& b) {
+      return a.n_blocks * a.nq > b.n_blocks * b.nq;
+    });
   }
   int upload() {
     release();
@@ -203,6 +261,9 @@ static int build_text_dependent(vb_plan* pl) {
     pl->sliding.runs.push_back({0, S + tv});
     pl->sliding.add_query_range(S, tv, run_begin, 1, S + tv);
   }
+  pl->full.finalize();
+  pl->coreset.finalize();
+  pl->sliding.finalize();
   if (pl->has_device) {
     int rc;
     if ((rc = pl->full.upload()) != VB_OK) return rc;
@@ -396,6 +457,7 @@ int vb_plan_export(const vb_plan* pl, int what, void* dst, int64_t* bytes) {
     case VB_EXPORT_TILE_MAP: src = pl->tile_map.data(); n = pl->tile_map.size() * sizeof(int32_t); break;
     case VB_EXPORT_TILE_WINDOW: src = pl->tile_window.data(); n = pl->tile_window.size() * sizeof(int32_t); break;
     case VB_EXPORT_SLIDING_RUNS: src = pl->sliding.runs.data(); n = pl->sliding.runs.size() * sizeof(KvRun); break;
+    case VB_EXPORT_SLIDING_ITEMS: src = pl->sliding.pairs.data(); n = pl->sliding.pairs.size() * sizeof(QPair); break;
     default: VB_REQUIRE(false, VB_ERR_INVALID, "unknown plan export %d", what);
   }
   if (dst != nullptr) {
@@ -427,7 +489,7 @@ int vb_coreset_select(const vb_plan* pl, const void* x, int64_t stride_b, int64_
   SelectParams p;
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.stride_b = stride_b; p.stride_h = stride_h; p.stride_s = stride_s;
-  p.center_tok = pl->d_center_tok; p.margin_tok = pl->d_margin_tok; p.head_list = nullptr;
+  p.center_tok = pl->d_center_tok; p.margin_tok = pl->d_margin_tok; p.head_list.used = 0;
   p.batch = batch; p.heads = heads; p.G = pl->G; p.n_margin = pl->g - 1; p.n_unpooled = pl->n_u;
   p.seq_len = pl->S; p.text_len = pl->d.text_len;
   p.unpooled_argsort = unpooled_argsort; p.pooled_argsort = pooled_argsort;
@@ -465,7 +527,7 @@ int vb_gather_rows(const void* src, int64_t src_stride_b, int64_t src_stride_h, 
   p.src_stride[0][0] = src_stride_b; p.src_stride[0][1] = src_stride_h; p.src_stride[0][2] = src_stride_s;
   p.dst_stride[0] = dst_stride_b; p.dst_stride[1] = dst_stride_h; p.dst_stride[2] = dst_stride_s;
   p.map = map; p.map_stride_b = map_stride_b; p.map_stride_h = map_stride_h;
-  p.head_list = nullptr; p.n_tensors = 1; p.batch = batch; p.heads = heads; p.n_rows = n_rows;
+  p.head_list.used = 0; p.n_tensors = 1; p.batch = batch; p.heads = heads; p.n_rows = n_rows;
   int rc = launch_gather_rows(p, static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
@@ -484,7 +546,6 @@ int64_t vb_attn_workspace_bytes(const vb_plan* pl, int32_t batch, int32_t heads)
   bytes += 3 * align_up(bh * rows_c * kHeadDim * 2, 1024);
   bytes += 2 * align_up(bh * rows_c * 4, 1024);                              // kept_tok for Q and K matchings
   bytes += 2 * align_up(bh * static_cast<int64_t>(pl->G) * std::max(pl->n_p, 1) * 4, 1024);   // dropped_tok
-  bytes += 2 * align_up(static_cast<int64_t>(heads) * 4, 1024);              // head lists
   return bytes + 4096;
 }
 
@@ -563,6 +624,7 @@ static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_
   if (n_used == 0) return VB_OK;
   VB_REQUIRE(n_ctas < (1ll << 31), VB_ERR_UNSUPPORTED, "attention grid too large");
   p.n_seg = n_used;
+  p.n_items = static_cast<int32_t>(n_ctas);
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.out_stride_b = a.out_stride[0]; p.out_stride_h = a.out_stride[1]; p.out_stride_s = a.out_stride[2];
   p.out_peer_count = a.out_peer_count;
@@ -619,6 +681,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   VB_REQUIRE(a.weights != nullptr || a.branch != nullptr, VB_ERR_INVALID, "need branch ids or blend weights");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool blend = a.weights != nullptr;
+  NvtxRange nvtx_layer(blend ? "vb_attn_fwd (blend)" : "vb_attn_fwd (top-1)");
   const int S = pl->S, TL = pl->d.text_len, TV = pl->d.text_valid;
   const int N = S + TL;
 
@@ -651,10 +714,12 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     }
     return v;
   };
-  auto upload_heads = [&](const std::vector<int32_t>& hs, int32_t** d_list) -> int {
-    *d_list = static_cast<int32_t*>(ws.take(static_cast<int64_t>(hs.size()) * 4));
-    VB_REQUIRE(*d_list != nullptr, VB_ERR_INVALID, "workspace exhausted");
-    VB_CUDA_OK(cudaMemcpyAsync(*d_list, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, stream));
+  auto head_list_of = [&](const std::vector<int32_t>& hs, HeadList* out) -> int {
+    VB_REQUIRE(hs.size() <= static_cast<size_t>(kMaxHeads) && a.heads <= 256, VB_ERR_UNSUPPORTED,
+               "more than %d heads of one branch in a layer", kMaxHeads);
+    memset(out, 0, sizeof(*out));
+    out->used = 1;
+    for (size_t i = 0; i < hs.size(); ++i) out->h[i] = static_cast<uint8_t>(hs[i]);
     return VB_OK;
   };
   // blend weights differ per batch element; top-1 routing is shared by the batch (wan.py:398)
@@ -694,6 +759,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
 
   // ---------------- branch 1: coreset ----------------
   if (!by_branch[1].empty()) {
+    NvtxRange nvtx("vb: coreset select + pool");
     const std::vector<int32_t>& hs = by_branch[1];
     const int nh = static_cast<int>(hs.size());
     const int64_t rows = pl->S_c + TL;
@@ -706,14 +772,14 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     int32_t* kept_k = kept_q;
     const bool kv_from_k = (a.flags & VB_ATTN_CORESET_KV_FROM_K) != 0;
     if (kv_from_k) kept_k = static_cast<int32_t*>(ws.take(bh * rows * 4));
-    int32_t* d_heads = nullptr;
-    if ((rc = upload_heads(hs, &d_heads)) != VB_OK) return rc;
+    HeadList heads_c;
+    if ((rc = head_list_of(hs, &heads_c)) != VB_OK) return rc;
     VB_REQUIRE(pq && pk && pv && kept_q && drop_q && kept_k, VB_ERR_INVALID, "workspace exhausted");
 
     SelectParams sp;
     sp.x = static_cast<const __nv_bfloat16*>(a.q);
     sp.stride_b = a.q_stride[0]; sp.stride_h = a.q_stride[1]; sp.stride_s = a.q_stride[2];
-    sp.center_tok = pl->d_center_tok; sp.margin_tok = pl->d_margin_tok; sp.head_list = d_heads;
+    sp.center_tok = pl->d_center_tok; sp.margin_tok = pl->d_margin_tok; sp.head_list = heads_c;
     sp.batch = a.batch; sp.heads = nh; sp.G = pl->G; sp.n_margin = pl->g - 1; sp.n_unpooled = pl->n_u;
     sp.seq_len = S; sp.text_len = TL;
     sp.unpooled_argsort = nullptr; sp.pooled_argsort = nullptr; sp.kept_tok = kept_q; sp.dropped_tok = drop_q;
@@ -731,7 +797,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     memset(&gp, 0, sizeof(gp));
     gp.dst_stride[0] = nh * rows * kHeadDim; gp.dst_stride[1] = rows * kHeadDim; gp.dst_stride[2] = kHeadDim;
     gp.map_stride_b = nh * rows; gp.map_stride_h = rows;
-    gp.head_list = d_heads; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
+    gp.head_list = heads_c; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
     if (!kv_from_k) {
       gp.n_tensors = 3; gp.map = kept_q;
       gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = pq;
@@ -771,6 +837,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
 
   // ---------------- branch 2: sliding tile ----------------
   if (!by_branch[2].empty()) {
+    NvtxRange nvtx("vb: sliding tile-major layout");
     const std::vector<int32_t>& hs = by_branch[2];
     const int nh = static_cast<int>(hs.size());
     const int64_t rows = N;
@@ -778,8 +845,8 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     __nv_bfloat16* tq = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
     __nv_bfloat16* tk = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
     __nv_bfloat16* tv = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
-    int32_t* d_heads = nullptr;
-    if ((rc = upload_heads(hs, &d_heads)) != VB_OK) return rc;
+    HeadList heads_s;
+    if ((rc = head_list_of(hs, &heads_s)) != VB_OK) return rc;
     VB_REQUIRE(tq && tk && tv, VB_ERR_INVALID, "workspace exhausted");
     GatherParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -791,7 +858,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
       gp.src_stride[0][i] = a.q_stride[i]; gp.src_stride[1][i] = a.k_stride[i]; gp.src_stride[2][i] = a.v_stride[i];
     }
     gp.dst_stride[0] = nh * rows * kHeadDim; gp.dst_stride[1] = rows * kHeadDim; gp.dst_stride[2] = kHeadDim;
-    gp.head_list = d_heads; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
+    gp.head_list = heads_s; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
     if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
     ++g_launches;
     BranchLaunch bl;
@@ -806,6 +873,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   }
 
   if (n_deferred > 0) {
+    NvtxRange nvtx("vb: attention launch (full + coreset + sliding segments)");
     const Segment* order[kMaxSegments];
     for (int i = 0; i < n_deferred; ++i) order[i] = &deferred[i];
     if ((rc = launch_segments(order, n_deferred, a, 0, a.batch, stream)) != VB_OK) return rc;
@@ -827,20 +895,26 @@ int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const 
                   int32_t heads, int32_t n_q, int32_t n_k, vb_stream_t stream_) {
   VB_REQUIRE(q && k && v && out && q_stride && k_stride && v_stride && out_stride, VB_ERR_INVALID, "null argument");
   VB_REQUIRE(batch > 0 && heads > 0 && n_q > 0 && n_k > 0, VB_ERR_INVALID, "sizes must be positive");
-  static thread_local std::vector<std::pair<std::pair<int, int>, Schedule*>> cache;
+  struct DenseKey {
+    int dev, n_q, n_k;
+  };
+  static thread_local std::vector<std::pair<DenseKey, Schedule*>> cache;      // device tables: one entry per device
+  int dev = 0;
+  VB_CUDA_OK(cudaGetDevice(&dev));
   Schedule* sched = nullptr;
   for (auto& e : cache)
-    if (e.first.first == n_q && e.first.second == n_k) sched = e.second;
+    if (e.first.dev == dev && e.first.n_q == n_q && e.first.n_k == n_k) sched = e.second;
   if (sched == nullptr) {
     sched = new Schedule();
     sched->runs.push_back({0, n_k});
     sched->add_query_range(0, n_q, 0, 1, n_k);
+    sched->finalize();
     int rc = sched->upload();
     if (rc != VB_OK) {
       delete sched;
       return rc;
     }
-    cache.push_back({{n_q, n_k}, sched});
+    cache.push_back({DenseKey{dev, n_q, n_k}, sched});
   }
   vb_attn_args a;
   memset(&a, 0, sizeof(a));
@@ -856,6 +930,7 @@ int vb_attn_dense(const void* q, const void* k, const void* v, void* out, const 
   bl.sched = sched;
   std::vector<AttnHead> hs(heads);
   for (int h = 0; h < heads; ++h) hs[h] = AttnHead{h, h, 1.f, 0};
+  NvtxRange nvtx("vb_attn_dense");
   g_launch_kind = VB_TIMING_DENSE;
   const int rc = run_branch(bl, a, hs, 0, batch, static_cast<cudaStream_t>(stream_));
   g_launch_kind = VB_TIMING_ROUTED;
@@ -884,6 +959,16 @@ int vb_block_rmsnorm_rope(const void* x, const void* weight, const float* cos_ta
   VB_REQUIRE((cos_tab == nullptr) == (sin_tab == nullptr), VB_ERR_INVALID, "cos and sin tables come together");
   int rc = launch_rmsnorm_rope(x, weight, cos_tab, sin_tab, out, rows, dim, tokens_per_batch, eps,
                                static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+
+int vb_block_headnorm_rope(const void* x, const void* weight, const float* cos_tab, const float* sin_tab, void* out,
+                           int32_t batch, int32_t rows, int32_t heads, int32_t rope_rows, int32_t dst_rows,
+                           int32_t dst_row0, float eps, vb_stream_t stream) {
+  VB_REQUIRE(x && out, VB_ERR_INVALID, "null argument");
+  int rc = launch_headnorm_rope(x, weight, cos_tab, sin_tab, out, batch, rows, heads, rope_rows, dst_rows, dst_row0, eps,
+                                static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }

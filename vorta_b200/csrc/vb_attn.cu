@@ -23,6 +23,11 @@
 // softmax warps find S(j+1) complete when they finish block j and do not wait in steady state.  (With P aliased on S
 // and one S per tile the chain softmax -> PV -> QK was serial per tile: 1600 + 300 + 1024 cycles per block, tensor pipe
 // 61 % busy; profiles/r1g_timeline_dense16k.log vs r1l_timeline_decoupled.log.)
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "vb_common.cuh"
 #include "vb_ptx.cuh"
 
@@ -36,6 +41,7 @@ constexpr int kTmaWarp = kSoftmaxWarps;
 constexpr int kMmaWarp = kSoftmaxWarps + 1;
 constexpr int kMmaWarps = 2;                       // one issuer per query tile, on different schedulers
 constexpr int kAttnThreads = (kSoftmaxWarps + 1 + kMmaWarps) * 32;
+constexpr int kConsumerWarps = kSoftmaxWarps + kMmaWarps;   // warps that follow the producer's work-item queue
 #ifndef VB_POLY_GROUPS
 #define VB_POLY_GROUPS 0x02        // group 1 of every 8 groups of 4 keys: 1/8 of the exps on the FMA pipe (measured best of 0, 1/8, 2/8, 3/8)
 #endif
@@ -46,47 +52,60 @@ struct SmemLayout {
   uint8_t q[2 * kTileBytes];                 // two query tiles
   uint8_t kv[kNumSlots * kTileBytes];        // K/V ring
   uint64_t bar_q_full[2];
+  uint64_t bar_q_empty[2];      // every QK of the item that used Q_t completed: the next item's Q_t may land
   uint64_t bar_slot_full[kNumSlots];
   uint64_t bar_slot_empty[kNumSlots];
   uint64_t bar_s_full[2];
   uint64_t bar_p_half[2];
   uint64_t bar_p_ready[2];
   uint64_t bar_o_full[2];
+  uint64_t bar_o_free[2];       // the epilogue of tile t holds O_t in registers: PV(0) of the next item may overwrite it
   uint64_t bar_s_free;          // the shared S region has been loaded into registers by its tile's softmax warps
   uint64_t bar_qk_go[2];        // softmax of tile t passed the trigger point of its block: QK of the next block may issue
   uint64_t bar_pv_done[2];      // PV of tile t completed: P_t is free again and O_t is quiescent
+  uint64_t bar_item_full[2];    // the producer published the index of the CTA's next work item
+  uint64_t bar_item_empty[2];   // all 18 consumer warps have read it
+  int32_t item_idx[2];          // work-item queue (depth 2): item index, or -1 = no more work
   uint32_t tmem_base_slot;
-  KvRun runs[32];
   float xchg[2][2][kBlockM];                 // row max / row sum exchange between the two threads of a row
 };
 constexpr int kAttnSmemBytes = sizeof(SmemLayout);
 static_assert(kAttnSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
+// Walks the 128-key blocks of a run list that lives in global memory (<= a dozen 8-byte reads per work item, L1 hits
+// after the first role touched them).
 struct BlockWalker {
   const KvRun* runs;
-  int n_runs, r, off;
-  __device__ __forceinline__ BlockWalker(const KvRun* rr, int n) : runs(rr), n_runs(n), r(0), off(0) {}
+  int n_runs, r, off, start, len;
+  __device__ __forceinline__ BlockWalker(const KvRun* rr, int n) : runs(rr), n_runs(n), r(0), off(0), start(0), len(0) {
+    if (n > 0) fetch();
+  }
+  __device__ __forceinline__ void fetch() {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(runs + r));
+    start = v.x;
+    len = v.y;
+  }
   // next 128-key block: first key row and number of valid keys; false when exhausted
   __device__ __forceinline__ bool next(int& row0, int& valid) {
     while (r < n_runs) {
-      const int len = runs[r].len;
       if (off < len) {
-        row0 = runs[r].start + off;
+        row0 = start + off;
         valid = min(kBlockN, len - off);
         off += kBlockN;
         return true;
       }
       ++r;
       off = 0;
+      if (r < n_runs) fetch();
     }
     return false;
   }
 };
 
-#ifdef VB_TIMELINE               // perf experiment: clock stamps of CTA (0,0,0) -> p.dbg as int64[who][block][8]
+#ifdef VB_TIMELINE               // perf experiment: clock stamps of the first item of CTA 0 -> p.dbg as int64[who][block][8]
 #define VB_STAMP(who, j, slot)                                                                         \
   do {                                                                                                 \
-    if (p.dbg != nullptr && blockIdx.x == 0 && (j) < 64)         \
+    if (p.dbg != nullptr && item == 0 && (j) < 64)                                                     \
       reinterpret_cast<long long*>(p.dbg)[((who) * 64 + (j)) * 8 + (slot)] = clock64();                \
   } while (0)
 #else
@@ -95,12 +114,41 @@ struct BlockWalker {
 
 #define VB_EXP2(x) fast_exp2(x)
 
-__device__ __forceinline__ int count_blocks(const KvRun* runs, int n_runs) {
-  int n = 0;
-  for (int r = 0; r < n_runs; ++r) n += (runs[r].len + kBlockN - 1) / kBlockN;
-  return n;
+// Work item -> (segment, pair, head, batch); segments are laid out longest items first by the host.  Every role of the
+// CTA decodes the item itself (warp-uniform integer math + 48 bytes from global memory), so no hand-off is needed.
+struct Item {
+  int seg_idx, batch;
+  QPair pair;
+  AttnHead head;
+};
+__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+  Item it;
+  it.seg_idx = 0;
+  if (p.n_seg > 1 && item >= p.seg[1].cta_begin) it.seg_idx = 1;
+  if (p.n_seg > 2 && item >= p.seg[2].cta_begin) it.seg_idx = 2;
+  const AttnSeg& seg = p.seg[it.seg_idx];
+  const int local = item - seg.cta_begin;
+  const int4* src = reinterpret_cast<const int4*>(seg.pairs + local % seg.n_pairs);
+  int4* dst = reinterpret_cast<int4*>(&it.pair);
+  dst[0] = __ldg(src);
+  dst[1] = __ldg(src + 1);
+  dst[2] = __ldg(src + 2);
+  it.head = p.heads[seg.head0 + (local / seg.n_pairs) % seg.n_heads];
+  it.batch = local / (seg.n_pairs * seg.n_heads) + p.batch0;
+  return it;
 }
 
+// Persistent kernel, one CTA per SM.  Work items are handed out dynamically: the first item of CTA c is item c, every
+// further one comes from a global counter (the TMA producer fetches it and publishes it to the other 18 warps through a
+// two-entry queue in shared memory).  The host sorts items longest first, so this is greedy longest-processing-time
+// scheduling: a layer's full, coreset and sliding items differ ~10x in length, and a static round-robin measured 5-9 %
+// slower in-step (profiles/r2b_*).  The counter resets itself: n_items fetches in total, the last wraps it to 0.
+// All pipelines run THROUGH the
+// item boundary: the K/V ring and every mbarrier keep their running phase, the producer prefetches the next item's
+// K/V and Q while the current item drains, and the issuer puts QK(0) of the next item on the tensor pipe while the
+// softmax warps are still in the epilogue of the current one.  Per-item cost outside the steady state was ~11 us
+// (CTA launch, TMEM allocation, barrier init, cold Q/K loads, pipeline fill, epilogue) against 3.4 us of work for a
+// 512-key cross-attention item and 77 us for a Wan-14B sliding-tile item (profiles/r1t_attn_full_summary_wan14.md).
 __global__ void __launch_bounds__(kAttnThreads, 1)
 vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constant__ AttnParams p) {
   // Everything lives in dynamic shared memory (no static __shared__), so the operand area starts at the CTA's
@@ -115,24 +163,10 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
   uint64_t* bar_p_ready = sm.bar_p_ready;
   uint64_t* bar_o_full = sm.bar_o_full;
   uint32_t& tmem_base_slot = sm.tmem_base_slot;
-  KvRun* s_runs = sm.runs;
   float (*s_xchg)[2][kBlockM] = sm.xchg;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: role / address math in uniform registers
   const int lane = threadIdx.x & 31;
-  // linear CTA index -> (segment, pair, head, batch); segments are laid out longest CTAs first by the host
-  int seg_idx = 0;
-  if (p.n_seg > 1 && static_cast<int>(blockIdx.x) >= p.seg[1].cta_begin) seg_idx = 1;
-  if (p.n_seg > 2 && static_cast<int>(blockIdx.x) >= p.seg[2].cta_begin) seg_idx = 2;
-  const AttnSeg& seg = p.seg[seg_idx];
-  const int cta_local = static_cast<int>(blockIdx.x) - seg.cta_begin;
-  const QPair pair = seg.pairs[cta_local % seg.n_pairs];
-  const AttnHead head = p.heads[seg.head0 + (cta_local / seg.n_pairs) % seg.n_heads];
-  const int batch = cta_local / (seg.n_pairs * seg.n_heads) + p.batch0;
-  const int nq = pair.nq;
-  const CUtensorMap& tmap_q = tmaps.m[seg_idx][0];
-  const CUtensorMap& tmap_k = tmaps.m[seg_idx][1];
-  const CUtensorMap& tmap_v = tmaps.m[seg_idx][2];
 
   if ((smem_u32(smem_raw) & 1023u) != 0) {      // SWIZZLE_128B atoms are 8 rows x 128 B
     if (threadIdx.x == 0) printf("vb_attn_fwd_kernel: dynamic shared memory base is not 1024-byte aligned\n");
@@ -141,20 +175,23 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
   uint8_t* smem_q = sm.q;                       // 2 x 32 KB
   uint8_t* smem_kv = sm.kv;                     // kNumSlots x 32 KB
 
-  const int n_runs = min(pair.run_count, 32);
-  if (threadIdx.x < n_runs) s_runs[threadIdx.x] = seg.runs[pair.run_begin + threadIdx.x];
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_q_full[i], 1);
+      mbar_init(&sm.bar_q_empty[i], 1);
       mbar_init(&bar_s_full[i], 1);
       mbar_init(&bar_p_half[i], kBlockM);    // 4 warps: column half 0 of P stored
       mbar_init(&bar_p_ready[i], kBlockM);   // 4 warps: column half 1 of P stored
       mbar_init(&bar_o_full[i], 1);
+      mbar_init(&sm.bar_o_free[i], kSoftmaxWarps / 2);
     }
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(&bar_slot_full[i], 1);
-      mbar_init(&bar_slot_empty[i], nq);     // one commit per query tile that consumed the slot
+      mbar_init(&bar_slot_empty[i], 2);      // two commits per slot: one per tile that read it, or both by its only reader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.bar_item_full[i], 1);
+      mbar_init(&sm.bar_item_empty[i], kConsumerWarps);
     }
     mbar_init(&sm.bar_s_free, kSoftmaxWarps / 2);        // lane 0 of the 8 warps of the loading tile
     for (int i = 0; i < 2; ++i) {
@@ -164,9 +201,11 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
     fence_barrier_init();
   }
   if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
+    for (int i = 0; i < p.n_seg; ++i) {
+      tma_prefetch_desc(&tmaps.m[i][0]);
+      tma_prefetch_desc(&tmaps.m[i][1]);
+      tma_prefetch_desc(&tmaps.m[i][2]);
+    }
   }
   if (warp == kMmaWarp) {
     tmem_alloc(&tmem_base_slot, 512);
@@ -176,31 +215,67 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const int n_blocks = count_blocks(s_runs, n_runs);
+  // consumer side of the work-item queue: entry n lives in slot n & 1; -1 ends the loop (warp-uniform)
+  auto next_item = [&](uint32_t n) -> int {
+    mbar_wait(&sm.bar_item_full[n & 1u], (n >> 1) & 1u);
+    const int item = *reinterpret_cast<volatile int32_t*>(&sm.item_idx[n & 1u]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.bar_item_empty[n & 1u]);
+    return item;
+  };
 
   if (warp == kTmaWarp) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
-      for (int t = 0; t < nq; ++t) {
-        mbar_arrive_expect_tx(&bar_q_full[t], kTileBytes);
-        tma_load_4d(smem_q + t * kTileBytes, &tmap_q, &bar_q_full[t], 0, pair.q_row0[t], head.hk, batch);
-        tma_load_4d(smem_q + t * kTileBytes + kHalfBytes, &tmap_q, &bar_q_full[t], 64, pair.q_row0[t], head.hk,
-                    batch);
-      }
-      BlockWalker w(s_runs, n_runs);
-      int row0, valid;
-      uint32_t load_idx = 0;
-      while (w.next(row0, valid)) {
-#pragma unroll
-        for (int which = 0; which < 2; ++which, ++load_idx) {
+      uint32_t load_idx = 0;                 // position in the K/V ring, running through all items
+      uint32_t q_uses[2] = {0, 0};           // items that used Q_t so far
+      for (uint32_t n = 0;; ++n) {
+        // fetch and publish: the first item is the CTA index, the rest come from the self-resetting global counter
+        // (atomicInc wraps to 0 on the launch's n_items-th fetch: gridDim.x of the fetches are the "no more work" ones)
+        int item = static_cast<int>(blockIdx.x);
+        if (n > 0) item = static_cast<int>(gridDim.x + atomicInc(p.work_counter, static_cast<unsigned>(p.n_items - 1)));
+        if (item >= p.n_items) item = -1;
+        mbar_wait(&sm.bar_item_empty[n & 1u], ((n >> 1) & 1u) ^ 1u);
+        *reinterpret_cast<volatile int32_t*>(&sm.item_idx[n & 1u]) = item;
+        mbar_arrive(&sm.bar_item_full[n & 1u]);          // release semantics: the store above is visible to the waiters
+        if (item < 0) break;
+        const Item it = decode_item(p, item);
+        const AttnSeg& seg = p.seg[it.seg_idx];
+        const CUtensorMap* tmap_q = &tmaps.m[it.seg_idx][0];
+        const CUtensorMap* tmap_k = &tmaps.m[it.seg_idx][1];
+        const CUtensorMap* tmap_v = &tmaps.m[it.seg_idx][2];
+        const int nq = it.pair.nq, hk = it.head.hk, batch = it.batch;
+        auto load_kv = [&](const CUtensorMap* m, int row0) {
           const uint32_t slot = load_idx % kNumSlots;
           const uint32_t phase = (load_idx / kNumSlots) & 1u;
           mbar_wait(&bar_slot_empty[slot], phase ^ 1u);
           mbar_arrive_expect_tx(&bar_slot_full[slot], kTileBytes);
-          const CUtensorMap* m = which == 0 ? &tmap_k : &tmap_v;
           uint8_t* dst = smem_kv + slot * kTileBytes;
-          tma_load_4d(dst, m, &bar_slot_full[slot], 0, row0, head.hk, batch);
-          tma_load_4d(dst + kHalfBytes, m, &bar_slot_full[slot], 64, row0, head.hk, batch);
+          tma_load_4d(dst, m, &bar_slot_full[slot], 0, row0, hk, batch);
+          tma_load_4d(dst + kHalfBytes, m, &bar_slot_full[slot], 64, row0, hk, batch);
+          ++load_idx;
+        };
+        auto load_q = [&]() {
+          for (int t = 0; t < nq; ++t) {
+            if (q_uses[t] > 0) mbar_wait(&sm.bar_q_empty[t], (q_uses[t] - 1) & 1u);
+            ++q_uses[t];
+            mbar_arrive_expect_tx(&bar_q_full[t], kTileBytes);
+            tma_load_4d(smem_q + t * kTileBytes, tmap_q, &bar_q_full[t], 0, it.pair.q_row0[t], hk, batch);
+            tma_load_4d(smem_q + t * kTileBytes + kHalfBytes, tmap_q, &bar_q_full[t], 64, it.pair.q_row0[t], hk, batch);
+          }
+        };
+        BlockWalker w0(seg.runs + it.pair.run_begin, it.pair.run_count);
+        BlockWalker w1(seg.runs + it.pair.run_begin2, it.pair.split ? it.pair.run_count2 : 0);
+        int row0, valid;
+        // the first K block does not depend on the previous item having released Q: request it first
+        for (int j = 0; w0.next(row0, valid); ++j) {
+          load_kv(tmap_k, row0);
+          if (j == 0) load_q();
+          load_kv(tmap_v, row0);
+          if (it.pair.split && w1.next(row0, valid)) {      // K1 V1 of the same block step
+            load_kv(tmap_k, row0);
+            load_kv(tmap_v, row0);
+          }
         }
       }
     }
@@ -209,84 +284,119 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
     // The whole warp runs this role converged and every address below is made warp-uniform, so descriptors live
     // in uniform registers and one elected lane issues; a single-lane role pays a register->uniform "waterfall"
     // per operand (measured: ~250 SASS instructions per 16 MMAs, the round-1 bottleneck).
-    const int nblk = __shfl_sync(0xffffffffu, n_blocks, 0);
-    const int nq_u = __shfl_sync(0xffffffffu, nq, 0);
-    if (nblk > 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(kBlockM, kBlockN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
-      constexpr uint64_t desc_hi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
-      constexpr uint32_t lbo_k = 1u << 16;
-      constexpr uint32_t lbo_v = (kHalfBytes >> 4) << 16;
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t q_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_q) & 0x3FFFFu) >> 4, 0);
-      const uint32_t kv_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_kv) & 0x3FFFFu) >> 4, 0);
-      auto issue_qk = [&](int t, uint32_t slot) {
-        const uint32_t a0 = q_lo + t * (kTileBytes >> 4) + lbo_k;
-        const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_k;
+    constexpr uint32_t idesc_qk0 = umma_idesc_bf16(kBlockM, 0, 0, 0);       // N filled in per block (tails are narrower)
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(kBlockM, kHeadDim, 0, 1);
+    constexpr uint64_t desc_hi = static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+    constexpr uint32_t lbo_k = 1u << 16;
+    constexpr uint32_t lbo_v = (kHalfBytes >> 4) << 16;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t q_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_q) & 0x3FFFFu) >> 4, 0);
+    const uint32_t kv_lo = __shfl_sync(0xffffffffu, (smem_u32(smem_kv) & 0x3FFFFu) >> 4, 0);
+    const int t = warp - kMmaWarp;
+    auto issue_qk = [&](uint32_t slot, int n_keys) {     // n_keys: multiple of 16 (a run's tail block is narrower)
+      const uint32_t a0 = q_lo + t * (kTileBytes >> 4) + lbo_k;
+      const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_k;
+      const uint32_t idesc = idesc_qk0 | (static_cast<uint32_t>(n_keys >> 3) << 17);
 #pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k) {
-          const uint32_t off = (k >> 2) * (kHalfBytes >> 4) + (k & 3) * 2;
-          umma_ss(tb, desc_hi | (a0 + off), desc_hi | (b0 + off), idesc_qk, k > 0);
-        }
-      };
-      auto issue_pv = [&](int t, uint32_t slot, uint32_t accumulate, int half) {
-        const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_v;
-        const uint32_t d = tb + 2 * kBlockN + t * kHeadDim;
-        const uint32_t a = tb + kBlockN + t * 64;
+      for (int k = 0; k < kHeadDim / 16; ++k) {
+        const uint32_t off = (k >> 2) * (kHalfBytes >> 4) + (k & 3) * 2;
+        umma_ss(tb, desc_hi | (a0 + off), desc_hi | (b0 + off), idesc, k > 0);
+      }
+    };
+    // 16-key steps [4 half, 4 half + 4) clipped to k_steps; full blocks (k_steps == 8) take the unrolled path: the
+    // issuer crawls between MMA batches, every instruction it does not execute there is tensor-pipe time
+    auto issue_pv = [&](uint32_t slot, uint32_t accumulate, int half, int k_steps) {
+      const uint32_t b0 = kv_lo + slot * (kTileBytes >> 4) + lbo_v;
+      const uint32_t d = tb + 2 * kBlockN + t * kHeadDim;
+      const uint32_t a = tb + kBlockN + t * 64;
+      if (k_steps == kBlockN / 16) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 32; ++kk) {
-          const int k = half * (kBlockN / 32) + kk;
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = half * 4 + kk;
           umma_ts(d, a + k * 8, desc_hi | (b0 + k * (2048 >> 4)), idesc_pv, accumulate | (k > 0));
         }
-      };
-      // One issuer warp per query tile, on different schedulers: an issuer shares its scheduler with four busy softmax
-      // warps and crawls through the ~40 instructions between two MMA batches (measured 220-600 cycles); with two
-      // issuers one tile's gap overlaps the other tile's batch (one issuer for both tiles: 1230 TFLOP/s dense, two:
-      // 1415; a polling event loop instead of in-order suspended waits starved completely: 1167).  Each issues, in
-      // order, QK_t(0), then per block QK_t(j+1) and PV_t(j) in two halves of 64 keys.
-      // The S region alternates strictly between the tiles through bar_s_free: use number u = nq * j + t waits for
-      // completion u - 1.
-      const int t = warp - kMmaWarp;
-      if (t < nq_u) {
-        mbar_wait(&bar_q_full[t], 0);
-        auto do_qk = [&](int j) {
-          const uint32_t k_idx = 2 * j, k_slot = k_idx % kNumSlots, k_phase = (k_idx / kNumSlots) & 1u;
-          const int use = nq_u * j + t;
-          if (j > 0) mbar_wait(&sm.bar_qk_go[t], (j - 1) & 1);
-          if (use > 0) mbar_wait(&sm.bar_s_free, (use - 1) & 1);
+      } else {
+        for (int k = half * 4; k < min(k_steps, half * 4 + 4); ++k)
+          umma_ts(d, a + k * 8, desc_hi | (b0 + k * (2048 >> 4)), idesc_pv, accumulate | (k > 0));
+      }
+    };
+    // One issuer warp per query tile, on different schedulers: an issuer shares its scheduler with four busy softmax
+    // warps and crawls through the ~40 instructions between two MMA batches (measured 220-600 cycles); with two
+    // issuers one tile's gap overlaps the other tile's batch (one issuer for both tiles: 1230 TFLOP/s dense, two:
+    // 1415; a polling event loop instead of in-order suspended waits starved completely: 1167).  Each issues, in
+    // order, QK_t(0), then per block QK_t(j+1) and PV_t(j) in two halves of 64 keys.
+    // The S region alternates strictly between the tiles through bar_s_free: use number u waits for completion u - 1.
+    uint32_t ring0 = 0;      // K/V ring index of the item's first load
+    uint32_t use0 = 0;       // S-region use number of the item's first QK
+    uint32_t blk = 0;        // blocks this tile has processed so far (phase of its per-block barriers)
+    uint32_t items_t = 0;    // items this tile has processed so far
+    for (uint32_t n = 0;; ++n) {
+      const int item = next_item(n);
+      if (item < 0) break;
+      const Item it = decode_item(p, item);
+      const AttnSeg& seg = p.seg[it.seg_idx];
+      const int nq = it.pair.nq, nblk = it.pair.n_blocks, split = it.pair.split;
+      const uint32_t ring_stride = split ? 4u : 2u, ring_off = split ? 2u * t : 0u;
+      const uint32_t empties = (nq == 2 && !split) ? 1u : 2u;      // commits this issuer owes a slot it read
+      if (t < nq) {
+        BlockWalker w(seg.runs + (split && t == 1 ? it.pair.run_begin2 : it.pair.run_begin),
+                      split && t == 1 ? it.pair.run_count2 : it.pair.run_count);
+        int row0, valid_next = 0, valid_cur = 0;
+        w.next(row0, valid_next);
+        mbar_wait(&bar_q_full[t], items_t & 1u);
+        auto do_qk = [&](int j, int valid) {
+          const uint32_t k_idx = ring0 + ring_stride * j + ring_off, k_slot = k_idx % kNumSlots,
+                         k_phase = (k_idx / kNumSlots) & 1u;
+          const uint32_t use = use0 + nq * j + t;
+          if (blk + j > 0) mbar_wait(&sm.bar_qk_go[t], (blk + j - 1) & 1u);
+          if (use > 0) mbar_wait(&sm.bar_s_free, (use - 1) & 1u);
           mbar_wait(&bar_slot_full[k_slot], k_phase);
           tc_fence_after();
           if (lane == 0) VB_STAMP(2 + t, j, 0);
           if (elect_one()) {
-            issue_qk(t, k_slot);
+            issue_qk(k_slot, (valid + 15) & ~15);
             umma_commit(&bar_s_full[t]);
             umma_commit(&bar_slot_empty[k_slot]);
+            if (empties == 2) umma_commit(&bar_slot_empty[k_slot]);
+            if (j == nblk - 1) umma_commit(&sm.bar_q_empty[t]);
           }
           __syncwarp();
           if (lane == 0) VB_STAMP(2 + t, j, 3);
         };
-        do_qk(0);
+        do_qk(0, valid_next);
         for (int j = 0; j < nblk; ++j) {
-          const uint32_t v_idx = 2 * j + 1, v_slot = v_idx % kNumSlots, v_phase = (v_idx / kNumSlots) & 1u;
-          if (j + 1 < nblk) do_qk(j + 1);
+          const uint32_t v_idx = ring0 + ring_stride * j + ring_off + 1, v_slot = v_idx % kNumSlots,
+                         v_phase = (v_idx / kNumSlots) & 1u;
+          valid_cur = valid_next;
+          if (j + 1 < nblk) {
+            w.next(row0, valid_next);
+            do_qk(j + 1, valid_next);
+          }
+          const int k_steps = (valid_cur + 15) >> 4;           // 16-key steps that hold real keys (tail blocks: < 8)
           mbar_wait(&bar_slot_full[v_slot], v_phase);
-          mbar_wait(&bar_p_half[t], j & 1);
+          mbar_wait(&bar_p_half[t], (blk + j) & 1u);
+          if (j == 0 && items_t > 0) mbar_wait(&sm.bar_o_free[t], (items_t - 1) & 1u);
           tc_fence_after();
           if (lane == 0) VB_STAMP(2 + t, j, 1);
-          if (elect_one()) issue_pv(t, v_slot, j > 0, 0);
+          if (elect_one()) issue_pv(v_slot, j > 0, 0, k_steps);
           __syncwarp();
-          mbar_wait(&bar_p_ready[t], j & 1);
+          mbar_wait(&bar_p_ready[t], (blk + j) & 1u);
           tc_fence_after();
           if (elect_one()) {
-            issue_pv(t, v_slot, j > 0, 1);
+            issue_pv(v_slot, j > 0, 1, k_steps);
             umma_commit(&sm.bar_pv_done[t]);
             umma_commit(&bar_slot_empty[v_slot]);
+            if (empties == 2) umma_commit(&bar_slot_empty[v_slot]);
             if (j == nblk - 1) umma_commit(&bar_o_full[t]);
           }
           __syncwarp();
           if (lane == 0) VB_STAMP(2 + t, j, 2);
         }
+        blk += nblk;
+        ++items_t;
       }
+      ring0 += ring_stride * nblk;
+      use0 += nq * nblk;
     }
   } else {
     // ============================ softmax / correction / epilogue ===============================
@@ -299,19 +409,32 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
     const int q4 = warp & 3;
     const int row = (q4 << 5) + lane;               // query row inside the tile == TMEM lane
     const int pair_bar = 1 + t * 4 + q4;            // named barrier of the two warps sharing these rows
-    if (t < nq && n_blocks > 0) {
-      const uint32_t lane_addr = static_cast<uint32_t>(q4 << 5) << 16;
-      const uint32_t s_addr = tmem_base + lane_addr;                              // S region shared by both tiles
-      const uint32_t p_addr = tmem_base + lane_addr + kBlockN + t * 64 + h * 32;  // P_t: its own 64 columns
-      const uint32_t o_addr = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim + h * 64;
-      const float scale = p.scale_log2;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 << 5) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr;                              // S region shared by both tiles
+    const uint32_t p_addr = tmem_base + lane_addr + kBlockN + t * 64 + h * 32;  // P_t: its own 64 columns
+    const uint32_t o_addr = tmem_base + lane_addr + 2 * kBlockN + t * kHeadDim + h * 64;
+    const float scale = p.scale_log2;
+    uint32_t blk = 0;        // blocks this tile has processed so far
+    uint32_t items_t = 0;    // items this tile has processed so far
+    for (uint32_t n = 0;; ++n) {
+      const int item = next_item(n);
+      if (item < 0) break;
       float m_ref = 0.f, l_sum = 0.f;
-
-      BlockWalker w(s_runs, n_runs);
+      const KvRun* run_ptr;
+      int run_cnt;
+      {   // only the run list is needed inside the block loop: the rest of the item is decoded again in the epilogue
+          // instead of being carried through the loop in registers (the loop body sits at the register cap)
+        const Item it = decode_item(p, item);
+        if (t >= it.pair.nq) continue;
+        const bool second = it.pair.split && t == 1;
+        run_ptr = p.seg[it.seg_idx].runs + (second ? it.pair.run_begin2 : it.pair.run_begin);
+        run_cnt = second ? it.pair.run_count2 : it.pair.run_count;
+      }
+      BlockWalker w(run_ptr, run_cnt);
       int row0, valid;
-      for (int j = 0; w.next(row0, valid); ++j) {
+      for (int j = 0; w.next(row0, valid); ++j, ++blk) {
         if (row == 0 && h == 0) VB_STAMP(t, j, 0);
-        mbar_wait(&bar_s_full[t], j & 1);
+        mbar_wait(&bar_s_full[t], blk & 1u);
         tc_fence_after();
         if (row == 0 && h == 0) VB_STAMP(t, j, 1);
         uint32_t s[2][32];
@@ -322,16 +445,8 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.bar_s_free);      // the S region may be overwritten by the next QK
         if (row == 0 && h == 0) VB_STAMP(t, j, 2);
-#if defined(VB_DEBUG_DUMP) && !defined(VB_TIMELINE)   // bring-up builds only: costs ~4 % in the product kernel
-        if (p.dbg != nullptr && j == 0 && blockIdx.x == 0) {
-          float* d = p.dbg + (static_cast<size_t>(t) * kBlockM + row) * kBlockN + h * 64;   // raw scores of block 0
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(s[c][i]);
-        }
-#endif
-        if (valid < kBlockN) {   // run tail: keys beyond the run do not exist for this query
+        if (valid < kBlockN) {   // run tail: keys beyond the run do not exist for this query (the QK of a tail block is
+                                 // issued for the valid keys rounded up to 16 only: the columns behind hold stale scores)
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -352,7 +467,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         s_xchg[t][h][row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         named_bar_sync(pair_bar, 64);
         const float m_new = fmaxf(s_xchg[t][0][row], s_xchg[t][1][row]) * scale;   // block has >= 1 valid key: finite
-        if (j + 1 < n_blocks && lane == 0) mbar_arrive(&sm.bar_qk_go[t]);          // QK_t(j+1) may issue now
+        if (lane == 0) mbar_arrive(&sm.bar_qk_go[t]);          // the next QK of this tile (next block or next item) may issue
         if (row == 0 && h == 0) VB_STAMP(t, j, 6);
 
         if (j == 0) {
@@ -367,7 +482,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
             }
             // O_t must be quiescent: PV_t(j-1) may still be in flight (QK_t(j) was issued before it), PV_t(j) cannot
             // start before BOTH halves have arrived below.  Each thread rescales its 64 channels.
-            mbar_wait(&sm.bar_pv_done[t], (j - 1) & 1);
+            mbar_wait(&sm.bar_pv_done[t], (blk - 1) & 1u);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
@@ -384,52 +499,62 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
           }
         }
 
-        // p = exp2(s * scale - m_ref): packed fp32x2 FMA / ADD (one issue slot per two keys), MUFU ex2 per key
-        const float neg_m = -m_ref;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-        uint32_t pk[32];
+        {
+          // p = exp2(s * scale - m_ref): packed fp32x2 FMA / ADD (one issue slot per two keys), MUFU ex2 per key
+          const float neg_m = -m_ref;
+          float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+          uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 2; ++c) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float x0, x1, x2, x3;
-            ffma2(x0, x1, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]), scale, scale, neg_m, neg_m);
-            ffma2(x2, x3, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]), scale, scale, neg_m, neg_m);
-            float e0, e1, e2, e3;
-            if ((kPolyGroups >> (i >> 2)) & 1) {      // compile-time pattern: this group of 4 keys skips the MUFU
-              exp2_poly2(x0, x1, e0, e1);
-              exp2_poly2(x2, x3, e2, e3);
-            } else {
-              e0 = VB_EXP2(x0); e1 = VB_EXP2(x1); e2 = VB_EXP2(x2); e3 = VB_EXP2(x3);
+            for (int i = 0; i < 32; i += 4) {
+              float x0, x1, x2, x3;
+              ffma2(x0, x1, __uint_as_float(s[c][i + 0]), __uint_as_float(s[c][i + 1]), scale, scale, neg_m, neg_m);
+              ffma2(x2, x3, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]), scale, scale, neg_m, neg_m);
+              float e0, e1, e2, e3;
+              if ((kPolyGroups >> (i >> 2)) & 1) {      // compile-time pattern: this group of 4 keys skips the MUFU
+                exp2_poly2(x0, x1, e0, e1);
+                exp2_poly2(x2, x3, e2, e3);
+              } else {
+                e0 = VB_EXP2(x0); e1 = VB_EXP2(x1); e2 = VB_EXP2(x2); e3 = VB_EXP2(x3);
+              }
+              fadd2(sum0, sum1, sum0, sum1, e0, e1);
+              fadd2(sum2, sum3, sum2, sum3, e2, e3);
+              pk[c * 16 + (i >> 1) + 0] = pack_bf16x2(e0, e1);
+              pk[c * 16 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
             }
-            fadd2(sum0, sum1, sum0, sum1, e0, e1);
-            fadd2(sum2, sum3, sum2, sum3, e2, e3);
-            pk[c * 16 + (i >> 1) + 0] = pack_bf16x2(e0, e1);
-            pk[c * 16 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
-          }
 #ifdef VB_TIMELINE
-          if (c == 0) { asm volatile("" ::: "memory"); if (row == 0 && h == 0) VB_STAMP(t, j, 7); }
+            if (c == 0) { asm volatile("" ::: "memory"); if (row == 0 && h == 0) VB_STAMP(t, j, 7); }
 #endif
+          }
+          if (blk > 0) {                     // the previous P_t (previous block or previous item) must have been consumed
+            mbar_wait(&sm.bar_pv_done[t], (blk - 1) & 1u);
+            tc_fence_after();
+          }
+          tmem_st32(p_addr, pk);            // P_t(j): keys [64 h, 64 h + 64) -> 32 columns of bf16 pairs
+          l_sum += (sum0 + sum1) + (sum2 + sum3);
+          if (row == 0 && h == 0) VB_STAMP(t, j, 3);
+          tmem_st_wait();
+          if (row == 0 && h == 0) VB_STAMP(t, j, 4);
         }
-        if (j > 0) {                       // P_t(j-1) must have been consumed before it is overwritten
-          mbar_wait(&sm.bar_pv_done[t], (j - 1) & 1);
-          tc_fence_after();
-        }
-        tmem_st32(p_addr, pk);            // P_t(j): keys [64 h, 64 h + 64) -> 32 columns of bf16 pairs
-        l_sum += (sum0 + sum1) + (sum2 + sum3);
-        if (row == 0 && h == 0) VB_STAMP(t, j, 3);
-        tmem_st_wait();
-        if (row == 0 && h == 0) VB_STAMP(t, j, 4);
         tc_fence_before();
         mbar_arrive(h == 0 ? &bar_p_half[t] : &bar_p_ready[t]);   // PV over keys [0,64) / [64,128) may start
         if (row == 0 && h == 0) VB_STAMP(t, j, 5);
       }
 
       // ------------------------------------ epilogue ------------------------------------
+      int item_again = item;
+      asm volatile("" : "+r"(item_again));         // opaque copy: keeps the decode below from being hoisted above the loop
+      const Item it = decode_item(p, item_again);
+      const AttnSeg& seg = p.seg[it.seg_idx];
+      const QPair& pair = it.pair;
+      const AttnHead& head = it.head;
+      const int batch = it.batch;
       s_xchg[t][h][row] = l_sum;
       named_bar_sync(pair_bar, 64);
       l_sum = s_xchg[t][0][row] + s_xchg[t][1][row];
-      mbar_wait(&bar_o_full[t], 0);
+      named_bar_sync(pair_bar, 64);               // both threads of the row have read: the next item may reuse xchg
+      mbar_wait(&bar_o_full[t], items_t & 1u);
       tc_fence_after();
       const bool row_ok = row < pair.q_rows[t];
       const int krow = pair.q_row0[t] + row;      // row in kernel order
@@ -453,14 +578,11 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         uint32_t o[32];
         tmem_ld32(o_addr + c * 32, o);
         tmem_ld_wait();
-#if defined(VB_DEBUG_DUMP) && !defined(VB_TIMELINE)   // bring-up builds only: costs ~4 % in the product kernel
-        if (p.dbg != nullptr && blockIdx.x == 0) {
-          float* d = p.dbg + 2 * kBlockM * kBlockN + (static_cast<size_t>(t) * kBlockM + row) * kHeadDim + h * 64;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) d[c * 32 + i] = __uint_as_float(o[i]);   // un-normalised O
-          if (c == 0 && h == 0) p.dbg[4 * kBlockM * kBlockN + t * kBlockM + row] = l_sum;
+        if (c == 1) {                               // O_t is in registers: PV(0) of the next item may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.bar_o_free[t]);
         }
-#endif
         for (int dsti = 0; dsti < n_dst; ++dsti) {
           int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
           __nv_bfloat16* obase = p.out;
@@ -493,6 +615,7 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
           }
         }
       }
+      ++items_t;
     }
   }
 
@@ -546,17 +669,34 @@ int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int6
   return VB_OK;
 }
 
-// `params.seg[i].cta_begin` must already hold the prefix sums; n_ctas = total over the segments.
-int launch_attn(const AttnTmaps& tmaps, const AttnParams& params, int n_ctas, cudaStream_t stream) {
+// `params.seg[i].cta_begin` must already hold the prefix sums; n_items = total work items over the segments.  The grid
+// is one persistent CTA per SM (224 KB of shared memory: one CTA fits); VB_ATTN_GRID=items launches one CTA per item
+// instead (the round-1 schedule, kept for A/B measurements).
+int launch_attn(const AttnTmaps& tmaps, const AttnParams& params_in, int n_items, cudaStream_t stream) {
   static bool configured[64] = {false};      // the attribute is per device
+  static int sm_count[64] = {0};
+  // Work counters: every launch takes the next of kCounters self-resetting counters of its device, so launches that
+  // overlap on different streams never share one (a counter is reused kCounters launches later).
+  constexpr unsigned kCounters = 256;
+  static unsigned int* counters[64] = {nullptr};
+  static unsigned next_counter[64] = {0};
   int dev = 0;
   VB_CUDA_OK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  VB_REQUIRE(dev >= 0 && dev < 64, VB_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  if (!configured[dev]) {
     VB_CUDA_OK(cudaFuncSetAttribute(vb_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kAttnSmemBytes));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    VB_CUDA_OK(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    VB_CUDA_OK(cudaMalloc(&counters[dev], kCounters * sizeof(unsigned int)));
+    VB_CUDA_OK(cudaMemset(counters[dev], 0, kCounters * sizeof(unsigned int)));
+    configured[dev] = true;
   }
-  if (n_ctas == 0) return VB_OK;
+  if (n_items == 0) return VB_OK;
+  AttnParams params = params_in;
+  params.work_counter = counters[dev] + (next_counter[dev]++ % kCounters);
+  const char* grid_env = getenv("VB_ATTN_GRID");       // read per launch: perf scripts flip it between launches
+  const bool per_item = grid_env != nullptr && strcmp(grid_env, "items") == 0;
+  const int n_ctas = per_item ? n_items : std::min(n_items, sm_count[dev]);
   vb_attn_fwd_kernel<<<static_cast<unsigned>(n_ctas), kAttnThreads, kAttnSmemBytes, stream>>>(tmaps, params);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;

@@ -326,6 +326,103 @@ vb_rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// HunyuanVideo Q / K prologue (reference: vorta/attention/hunyuan.py:62-134): per-HEAD RMSNorm (norm_q / norm_k /
+// norm_added_q / norm_added_k are RMSNorm(128)) + real-valued RoPE on the video tokens only + placement of the row in
+// the joint [video | text] sequence, in ONE pass.  The reference runs this as a normalisation over a transposed
+// view, an unbind / stack / float-multiply RoPE and three torch.cat over the whole joint tensor (~10 HBM passes).
+//   unit = (row, head): a half-warp, 16 lanes x 16 bytes; 4 units in flight per half-warp
+//   src row r of batch b  ->  dst row dst_row0 + r of batch b  (dst has dst_rows rows per batch; in place allowed)
+//   rows r < rope_rows rotate channel pairs (2i, 2i+1) by (cos, sin)[r][i] (fp32 tables of 64 entries per token)
+// ------------------------------------------------------------------------------------------------
+struct HeadNormParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* weight;     // (128) or nullptr = no normalisation
+  const float* cs;                 // (rope_rows, 64) or nullptr
+  const float* sn;
+  __nv_bfloat16* out;
+  int64_t units;                   // batch * rows * heads
+  int rows, heads, rope_rows, dst_rows, dst_row0;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) vb_headnorm_rope_kernel(const HeadNormParams p) {
+  constexpr int kInFlight = 4;
+  const int lane16 = threadIdx.x & 15;
+  const int64_t hw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+  const int64_t n_hw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4;
+  float wv[8];
+  if (p.weight) unpack8(__ldg(reinterpret_cast<const uint4*>(p.weight) + lane16), wv);
+  // the loop bound is the same for both half-warps of a warp (the shuffles below are full-warp)
+  const int64_t n_steps = (p.units + n_hw * kInFlight - 1) / (n_hw * kInFlight);
+  for (int64_t step = 0; step < n_steps; ++step) {
+    const int64_t u0 = (step * n_hw + hw) * kInFlight;
+    uint4 raw[kInFlight];
+#pragma unroll
+    for (int i = 0; i < kInFlight; ++i) {
+      const int64_t u = u0 + i;
+      raw[i] = u < p.units ? (reinterpret_cast<const uint4*>(p.x) + u * 16)[lane16] : make_uint4(0, 0, 0, 0);   // plain load: x may alias out
+    }
+#pragma unroll
+    for (int i = 0; i < kInFlight; ++i) {
+      const int64_t u = u0 + i;
+      float f[8];
+      unpack8(raw[i], f);
+      float s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s2 = fmaf(f[e], f[e], s2);
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (u >= p.units) continue;
+      const int head = static_cast<int>(u % p.heads);
+      const int64_t rb = u / p.heads;
+      const int r = static_cast<int>(rb % p.rows);
+      const int64_t b = rb / p.rows;
+      if (p.weight) {
+        const float rinv = rsqrtf(s2 * (1.f / kHeadDim) + p.eps);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = f[e] * rinv * wv[e];
+      }
+      if (p.cs != nullptr && r < p.rope_rows) {
+        const float4 c4 = ldg4(p.cs + static_cast<int64_t>(r) * (kHeadDim / 2) + lane16 * 4);
+        const float4 s4 = ldg4(p.sn + static_cast<int64_t>(r) * (kHeadDim / 2) + lane16 * 4);
+        const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int pz = 0; pz < 4; ++pz) {
+          const float re = f[2 * pz], im = f[2 * pz + 1];
+          f[2 * pz] = re * cv[pz] - im * sv[pz];
+          f[2 * pz + 1] = re * sv[pz] + im * cv[pz];
+        }
+      }
+      const int64_t drow = b * p.dst_rows + p.dst_row0 + r;
+      reinterpret_cast<uint4*>(p.out)[(drow * p.heads + head) * 16 + lane16] = pack8(f);
+    }
+  }
+}
+
+int launch_headnorm_rope(const void* x, const void* weight, const float* cs, const float* sn, void* out, int batch,
+                         int rows, int heads, int rope_rows, int dst_rows, int dst_row0, float eps,
+                         cudaStream_t stream) {
+  VB_REQUIRE(batch >= 0 && rows >= 0 && heads > 0 && dst_row0 >= 0 && dst_row0 + rows <= dst_rows, VB_ERR_INVALID,
+             "headnorm_rope: rows [%d, %d) do not fit a destination of %d rows", dst_row0, dst_row0 + rows, dst_rows);
+  VB_REQUIRE((cs == nullptr) == (sn == nullptr) && rope_rows <= rows, VB_ERR_INVALID,
+             "headnorm_rope: cos / sin tables come together and cover at most the source rows");
+  HeadNormParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.weight = static_cast<const __nv_bfloat16*>(weight);
+  p.cs = cs; p.sn = sn;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.units = static_cast<int64_t>(batch) * rows * heads;
+  p.rows = rows; p.heads = heads; p.rope_rows = cs ? rope_rows : 0; p.dst_rows = dst_rows; p.dst_row0 = dst_row0;
+  p.eps = eps;
+  if (p.units == 0) return VB_OK;
+  const int64_t blocks_needed = (p.units / 4 * 16 + 255) / 256 + 1;
+  const int grid = static_cast<int>(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
+  vb_headnorm_rope_kernel<<<grid, 256, 0, stream>>>(p);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
 static unsigned row_grid(int64_t rows, int nv) {
   const int rows_per_cta = kRowCtaThreads / (32 * row_warps(nv));
   return static_cast<unsigned>((rows + rows_per_cta - 1) / rows_per_cta);

@@ -38,15 +38,23 @@ constexpr int kBlockN = 128;      // keys per MMA tile
 constexpr int kMaxHeads = 64;     // heads per attention launch
 constexpr int kMaxHeadTable = 128; // heads per Ulysses exchange (slot -> head table passed by value)
 
-// One CTA's work: up to two 128-row query tiles that share the same key/value run list.
+// One work item: up to two 128-row query tiles.  Normally both tiles attend to the SAME key/value run list (they are
+// neighbouring tiles of one logical query range) and every K/V block staged in shared memory feeds both.  A "split"
+// item (split != 0) pairs two single-tile leftovers of DIFFERENT ranges: tile 1 has its own run list (run_begin2 /
+// run_count2, same number of 128-key blocks), the K/V ring then carries K0 V0 K1 V1 per block step, and both tile
+// pipelines of the CTA stay busy where a single tile would leave one idle.
 struct QPair {
   int32_t q_row0[2];   // first row of each query tile, in kernel order
   int32_t q_rows[2];   // valid rows in each tile (<= 128)
-  int32_t run_begin;   // first entry in KvRun[]
+  int32_t run_begin;   // first entry in KvRun[] (tile 0, and tile 1 unless split)
   int32_t run_count;   // number of runs
   int32_t nq;          // 1 or 2
+  int32_t n_blocks;    // 128-key blocks of the run list (per tile)
+  int32_t split;       // 0: shared run list; 1: tile 1 uses run_begin2 / run_count2
+  int32_t run_begin2, run_count2;
   int32_t pad;
 };
+static_assert(sizeof(QPair) == 48, "QPair layout");
 // A contiguous range of keys (kernel order) every query of the pair attends to.
 struct KvRun {
   int32_t start;
@@ -74,7 +82,7 @@ struct AttnSeg {
   int32_t bcast_rows, bcast_n;
   int32_t n_pairs, n_heads;     // CTAs of the segment = n_pairs * n_heads * n_batch, pair index fastest
   int32_t head0;                // the segment's heads are AttnParams::heads[head0 .. head0 + n_heads)
-  int32_t cta_begin;            // linear CTA index of the segment's first CTA
+  int32_t cta_begin;            // linear item index of the segment's first work item
 };
 
 struct AttnParams {
@@ -85,6 +93,8 @@ struct AttnParams {
   __nv_bfloat16* out_peers[8];
   int32_t out_peer_count, out_peer_rows;
   float scale_log2;             // log2(e) / sqrt(D)
+  int32_t n_items;              // work items of the launch (all segments)
+  unsigned int* work_counter;   // device counter handing out items beyond the first gridDim.x; 0 before and after a launch
   int32_t n_seg;
   int32_t batch0;               // batch index of the first batch slice (blend mode launches one batch at a time)
   float* dbg;                   // optional debug dump (bring-up only), nullptr in production
@@ -97,13 +107,21 @@ struct AttnTmaps {
   CUtensorMap m[kMaxSegments][3];   // q, k, v of each segment
 };
 
+// Source head of each processed head slot, passed BY VALUE inside the launch parameters (<= 64 bytes): a layer's
+// head lists change with the routing of every layer and used to cost a pageable host->device copy each.
+struct HeadList {
+  uint8_t h[kMaxHeads];
+  int32_t used;                // 0 = identity (slot i reads head i)
+  __host__ __device__ int head(int slot) const { return used ? h[slot] : slot; }
+};
+
 // Coreset selection launch parameters (vb_kernels.cu)
 struct SelectParams {
   const __nv_bfloat16* x;
   int64_t stride_b, stride_h, stride_s;
   const int32_t* center_tok;   // (G)
   const int32_t* margin_tok;   // (G, g-1)
-  const int32_t* head_list;    // source head of each processed head slot, nullptr = identity
+  HeadList head_list;          // source head of each processed head slot
   int32_t batch, heads, G, n_margin, n_unpooled, seq_len, text_len;
   int64_t* unpooled_argsort;   // (B, heads, G, n_u)
   int64_t* pooled_argsort;     // (B, heads, G, n_margin - n_u)
@@ -129,7 +147,7 @@ struct GatherParams {
   int64_t dst_stride[3];      // b, h, s (shared by the tensors)
   const int32_t* map;
   int64_t map_stride_b, map_stride_h;
-  const int32_t* head_list;   // nullptr = identity
+  HeadList head_list;
   int32_t n_tensors, batch, heads, n_rows;
 };
 

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kSelectWarps * 32, 2) vb_coreset_select_kernel
     const int hs = static_cast<int>(unit % p.heads);
     const int grp = static_cast<int>((unit / p.heads) % p.G);
     const int b = static_cast<int>(unit / (static_cast<int64_t>(p.G) * p.heads));
-    const int h_src = p.head_list ? p.head_list[hs] : hs;
+    const int h_src = p.head_list.head(hs);
     const __nv_bfloat16* base = p.x + b * p.stride_b + h_src * p.stride_h;
     const int ctok = p.center_tok[grp];
     const int32_t* mtok = p.margin_tok + static_cast<int64_t>(grp) * p.n_margin;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) vb_gather_rows_kernel(const GatherParams 
         rr /= p.n_rows;
         const int hs = static_cast<int>(rr % p.heads);
         const int b = static_cast<int>(rr / p.heads);
-        const int h_src = p.head_list ? p.head_list[hs] : hs;
+        const int h_src = p.head_list.head(hs);
         const int src_row = p.map ? p.map[b * p.map_stride_b + hs * p.map_stride_h + i] : i;
         const __nv_bfloat16* s = p.src[t] + b * p.src_stride[t][0] + h_src * p.src_stride[t][1] +
                                  static_cast<int64_t>(src_row) * p.src_stride[t][2];

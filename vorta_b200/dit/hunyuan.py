@@ -83,8 +83,14 @@ class AdaLayerNormZero(nn.Module):
         self.norm = FP32LayerNorm(dim, eps=1e-6, elementwise_affine=False)
         self.n_out = n_out
 
-    def modulation(self, emb: torch.Tensor):
-        return self.linear(self.silu(emb)).float().chunk(self.n_out, dim=1)
+    def forward(self, x: torch.Tensor, emb: torch.Tensor):
+        """diffusers-style call (AdaLayerNormZero: norm(x) * (1 + scale) + shift and the remaining vectors); the routed
+        block forwards do not use it — they read ``silu`` / ``linear`` and fuse the normalisation."""
+        v = self.linear(self.silu(emb)).float().chunk(self.n_out, dim=1)
+        if self.n_out == 2:                       # AdaLayerNormContinuous: (scale, shift)
+            return (self.norm(x).float() * (1 + v[0][:, None]) + v[1][:, None]).to(x.dtype)
+        y = (self.norm(x).float() * (1 + v[1][:, None]) + v[0][:, None]).to(x.dtype)
+        return (y, *v[2:])
 
 
 class MLP(nn.Module):
@@ -139,6 +145,15 @@ class TimestepMLP(nn.Module):
         return self.linear_2(self.act(self.linear_1(x)))
 
 
+class TokenRefinerStandIn(TimestepMLP):
+    """Stand-in for diffusers' HunyuanVideoTokenRefiner with its call signature ``(hidden_states, timestep,
+    attention_mask)`` (reference call site: modeling_hunyuan.py:210).  The real refiner is a 2-block transformer over the
+    256 text tokens conditioned on the timestep — outside the routed-attention path; here it is a per-token MLP."""
+
+    def forward(self, hidden_states, timestep=None, attention_mask=None):
+        return super().forward(hidden_states)
+
+
 class HunyuanVideoConditionEmbedding(nn.Module):
     def __init__(self, cfg: HunyuanConfig):
         super().__init__()
@@ -161,7 +176,7 @@ class HunyuanDiT(nn.Module):
         self.config = cfg
         p, pt = cfg.patch_size, cfg.patch_size_t
         self.x_embedder = nn.Conv3d(cfg.in_channels, cfg.dim, kernel_size=(pt, p, p), stride=(pt, p, p))
-        self.context_embedder = TimestepMLP(cfg.text_embed_dim, cfg.dim)       # token-refiner stand-in
+        self.context_embedder = TokenRefinerStandIn(cfg.text_embed_dim, cfg.dim)
         self.time_text_embed = HunyuanVideoConditionEmbedding(cfg)
         self.rope = HunyuanVideoRotaryPosEmbed(cfg)
         self.transformer_blocks = nn.ModuleList([HunyuanVideoTransformerBlock(cfg) for _ in range(cfg.num_layers)])

@@ -402,3 +402,40 @@ def rmsnorm_rope(x: torch.Tensor, weight: torch.Tensor, eps: float, cos: Optiona
                                               sin.data_ptr() if sin is not None else None, out.data_ptr(), rows, dim,
                                               per_batch, float(eps), _stream_ptr(x.device)))
     return out
+
+
+def headnorm_rope(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float, heads: int,
+                  cos: Optional[torch.Tensor] = None, sin: Optional[torch.Tensor] = None,
+                  rope_rows: Optional[int] = None, out: Optional[torch.Tensor] = None, dst_row0: int = 0
+                  ) -> torch.Tensor:
+    """Per-head RMSNorm * weight (128), then RoPE on the first ``rope_rows`` rows, written into rows
+    [dst_row0, dst_row0 + rows) of ``out`` (B, dst_rows, heads * 128) — hunyuan.py:62-134 in one pass.
+    x: (B, rows, heads * 128) bf16 contiguous; cos / sin fp32 (>= rope_rows, 64).  ``out`` defaults to in place."""
+    if not x.is_cuda:
+        raise L.VortaB200Error("block kernels need CUDA tensors: vorta_b200 has no CPU path")
+    if x.dtype != torch.bfloat16 or x.dim() != 3 or not x.is_contiguous() or x.shape[2] != heads * HEAD_DIM:
+        raise ValueError(f"headnorm_rope needs a contiguous bf16 (B, rows, {heads * HEAD_DIM}) tensor, got {tuple(x.shape)}")
+    B, rows, _ = x.shape
+    if out is None:
+        out = x
+    if (out.dtype != torch.bfloat16 or out.dim() != 3 or not out.is_contiguous() or out.shape[0] != B
+            or out.shape[2] != x.shape[2]):
+        raise ValueError("headnorm_rope: out must be a contiguous bf16 (B, dst_rows, heads * 128) tensor")
+    w = None
+    if weight is not None:
+        w = weight if weight.dtype == torch.bfloat16 and weight.is_contiguous() else weight.to(torch.bfloat16).contiguous()
+        if w.numel() != HEAD_DIM:
+            raise ValueError(f"per-head RMSNorm weight must have {HEAD_DIM} entries, got {w.numel()}")
+    n_rope = 0
+    if cos is not None:
+        n_rope = rows if rope_rows is None else int(rope_rows)
+        if cos.dtype != torch.float32 or sin.dtype != torch.float32 or cos.shape[-1] != HEAD_DIM // 2 or \
+                cos.shape[0] < n_rope or not cos.is_contiguous() or not sin.is_contiguous():
+            raise ValueError(f"cos / sin tables must be contiguous fp32 (>= {n_rope}, {HEAD_DIM // 2})")
+    with torch.cuda.device(x.device):
+        L.check(L.lib().vb_block_headnorm_rope(x.data_ptr(), w.data_ptr() if w is not None else None,
+                                               cos.data_ptr() if cos is not None else None,
+                                               sin.data_ptr() if cos is not None else None, out.data_ptr(), B, rows,
+                                               heads, n_rope, out.shape[1], int(dst_row0), float(eps),
+                                               _stream_ptr(x.device)))
+    return out

@@ -52,6 +52,14 @@ def hunyuan_combined_embedding_forward(self, timestep, pooled_projection, guidan
     return conditioning, None, timesteps_emb
 
 
+def _ada_chunks(norm, emb: torch.Tensor, n: int):
+    """The n fp32 modulation vectors of an adaptive LayerNorm module, through the members diffusers' AdaLayerNormZero
+    (6), AdaLayerNormZeroSingle (3) and AdaLayerNormContinuous (2: scale, shift) all have — ``silu`` and ``linear`` — so
+    the fused block forwards work on the diffusers model as well as on ``vorta_b200.dit.HunyuanDiT``; the LayerNorm
+    itself is applied by ``ops.ln_modulate`` (reference call sites: modeling_hunyuan.py:146, 471, 538-539)."""
+    return norm.linear(norm.silu(emb)).float().chunk(n, dim=1)
+
+
 def _attn_kwargs(self_attention_kwargs, routing_score, branch):
     kw = dict(self_attention_kwargs or {})
     kw["routing_score"] = routing_score
@@ -65,8 +73,8 @@ def hunyuan_dual_block_routed_forward(self, hidden_states, encoder_hidden_states
                                       use_original_attn: bool = False, self_attention_kwargs=None,
                                       clean_timesteps_emb=None, routing_score=None, branch=None):
     """Dataflow of :524-590 with every elementwise stage as one fused pass."""
-    shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.norm1.modulation(temb)
-    c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = self.norm1_context.modulation(temb)
+    shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = _ada_chunks(self.norm1, temb, 6)
+    c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = _ada_chunks(self.norm1_context, temb, 6)
     norm_hidden = ops.ln_modulate(hidden_states, None, None, scale_msa, shift_msa, 1e-6)
     norm_encoder = ops.ln_modulate(encoder_hidden_states, None, None, c_scale_msa, c_shift_msa, 1e-6)
     if use_original_attn:
@@ -94,7 +102,7 @@ def hunyuan_single_block_routed_forward(self, hidden_states, encoder_hidden_stat
     """Dataflow of :452-521."""
     text_len = encoder_hidden_states.shape[1]
     residual = torch.cat([hidden_states, encoder_hidden_states], dim=1)
-    shift, scale, gate = self.norm.modulation(temb)
+    shift, scale, gate = _ada_chunks(self.norm, temb, 3)
     norm = ops.ln_modulate(residual, None, None, scale, shift, 1e-6)
     mlp = torch._addmm_activation(self.proj_mlp.bias, norm.flatten(0, 1), self.proj_mlp.weight.t(),
                                   use_gelu=True).unflatten(0, norm.shape[:2])
@@ -132,7 +140,7 @@ def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, tim
     image_rotary_emb = self.rope(hidden_states)
     temb, token_replace_emb, clean_emb = self.time_text_embed(timestep, pooled_projections, guidance)
     hidden_states = self.x_embedder(hidden_states).flatten(2).transpose(1, 2).contiguous()
-    encoder_hidden_states = self.context_embedder(encoder_hidden_states)
+    encoder_hidden_states = self.context_embedder(encoder_hidden_states, timestep, encoder_attention_mask)   # :210
 
     latent_len, text_len = hidden_states.shape[1], encoder_hidden_states.shape[1]
     if SP_STATE.enabled:        # token sharding of the video stream; the text stream is replicated
@@ -173,7 +181,7 @@ def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, tim
                     hidden_layer_distill_loss, F.mse_loss(ref_hidden_states.float(), hidden_states.float()))
     routing_scores = list(scores.detach().to(temb.dtype).cpu().unbind(0)) if return_routing_scores else []
 
-    scale, shift = self.norm_out.modulation(temb)
+    scale, shift = _ada_chunks(self.norm_out, temb, 2)
     hidden_states = self.proj_out(ops.ln_modulate(hidden_states, None, None, scale, shift, 1e-6))
     if return_losses:
         with torch.no_grad():

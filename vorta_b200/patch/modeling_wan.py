@@ -56,8 +56,11 @@ def wan_block_routed_forward(self, hidden_states, encoder_hidden_states, temb, r
     kwargs = dict(self_attention_kwargs or {})
     if branch is not None:
         kwargs["branch"] = branch
-    attn_output = self.attn1(hidden_states=norm_hidden_states, rotary_emb=rotary_emb, routing_score=routing_score,
-                             use_original_attn=use_original_attn, **kwargs)
+    if type(self.attn1.processor) is WanAttnProcessor2_0:     # dense baseline: the base processor takes no routing kwargs
+        attn_output = self.attn1(hidden_states=norm_hidden_states, rotary_emb=rotary_emb)
+    else:
+        attn_output = self.attn1(hidden_states=norm_hidden_states, rotary_emb=rotary_emb, routing_score=routing_score,
+                                 use_original_attn=use_original_attn, **kwargs)
     hidden_states = ops.gate_residual(hidden_states, attn_output, gate_msa)
 
     norm_hidden_states = ops.ln_modulate(hidden_states, self.norm2.weight, self.norm2.bias, None, None, self.norm2.eps)
@@ -102,15 +105,26 @@ def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timeste
     kwargs = dict(self_attention_kwargs or {})
     tau = kwargs.get("tau_sparse")
     eval_mode = isinstance(self.blocks[0].attn1.processor, WanAttnProcessorTripleEval)
+    # dense baseline (apply_sp_flashattn_transformer): plain processors, no routers; same token-sharded forward
+    dense_baseline = type(self.blocks[0].attn1.processor) is WanAttnProcessor2_0
     # routing of the whole step in one launch: it depends on temb only
-    if not eval_mode and torch.is_grad_enabled() and any(q.requires_grad for q in self.blocks[0].router.parameters()):
+    if not dense_baseline and not eval_mode and torch.is_grad_enabled() and any(q.requires_grad for q in self.blocks[0].router.parameters()):
         # the Train processors exist to fit the routers; that needs the backward of the attention kernels
         raise NotImplementedError("vorta_b200: router training is not supported yet (no attention backward); run the "
                                   "Train processors under torch.no_grad()")
-    scores, branches = route_step([b.router for b in self.blocks], temb, tau if eval_mode else None)
     reg_loss = hidden_layer_distill_loss = last_layer_distill_loss = None
+    if dense_baseline:
+        if return_losses or return_routing_scores:
+            raise ValueError("the dense baseline (apply_sp_flashattn_transformer) has no routers: no losses / scores")
+        scores = branches = None
+    else:
+        scores, branches = route_step([b.router for b in self.blocks], temb, tau if eval_mode else None)
     ref_hidden_states = hidden_states.detach().clone() if return_losses else None
     for i, block in enumerate(self.blocks):
+        if dense_baseline:
+            hidden_states, _ = block(hidden_states, encoder_hidden_states, timestep_proj, rotary_emb,
+                                     temb_before_proj=temb, use_original_attn=True)
+            continue
         score_i = scores[i].to(temb.dtype)
         hidden_states, _ = block(hidden_states, encoder_hidden_states, timestep_proj, rotary_emb,
                                  temb_before_proj=temb, use_original_attn=False, self_attention_kwargs=kwargs,
@@ -124,7 +138,7 @@ def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timeste
                 hidden_layer_distill_loss = accumulate_loss(
                     hidden_layer_distill_loss, F.mse_loss(ref_hidden_states.float(), hidden_states.float()))
     # one device -> host copy for the whole step (the reference copies per block, :119-120)
-    routing_scores = list(scores.detach().to(temb.dtype).cpu().unbind(0)) if return_routing_scores else []
+    routing_scores = list(scores.detach().to(temb.dtype).cpu().unbind(0)) if return_routing_scores else []     # noqa: E501
 
     shift, scale = ((self.scale_shift_table.float() + temb.float().unsqueeze(1))).unbind(dim=1)
     shift, scale = shift.contiguous(), scale.contiguous()
@@ -190,9 +204,14 @@ def apply_vorta_transformer(model, train_router: bool = False, checkpoint_file: 
 
 
 def apply_sp_flashattn_transformer(model):
-    """Baseline-only variant (modeling_wan.py:313-323): dense attention processors, no routing."""
+    """Baseline-only variant (modeling_wan.py:313-323): dense attention processors, no routing.  The reference leaves
+    the model forward alone because its PIPELINE shards frames (pipeline_wan.py:120-122); here sharding lives in the
+    model forward (tokens, not frames), so the baseline installs the same forward — every rank takes its S / P tokens,
+    the processors exchange heads for the full sequence, and the output is all-gathered."""
+    model.__class__.forward = wan_transformer_3d_routed_forward
     model.rope.__class__.forward = wan_rope_forward
     for block in model.blocks:
         block.attn1.set_processor(WanAttnProcessor2_0())
         block.attn2.set_processor(WanAttnProcessor2_0())
+        block.__class__.forward = wan_block_routed_forward
     return model
