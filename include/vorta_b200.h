@@ -104,6 +104,10 @@ int vb_plan_export(const vb_plan* plan, int what, void* dst, int64_t* bytes);
  *   w      (L, 3H, E), bias (L, 3H)   w_dtype
  *   scores (L, B, H, 3) fp32  out
  *   branch (L, H) int32 out: argmax_e scores[l, 0, h, e]; set to 0 when that score < tau (NaN tau: no threshold)
+ * w_dtype VB_DTYPE_F32: fp32 arithmetic throughout (the contract of north_star).  w_dtype VB_DTYPE_BF16 (the reference's
+ * inference default router_dtype): SiLU output, logits and scores are each rounded to bf16 as the reference's bf16
+ * modules do, and the decision is taken on the rounded scores (ties -> lowest expert index); scores stay an fp32
+ * buffer holding bf16-exact values.
  * ---------------------------------------------------------------------------------------------------- */
 int vb_router_forward(const void* temb, int temb_dtype, const void* w, const void* bias, int w_dtype,
                       int64_t w_layer_stride, int64_t bias_layer_stride, int32_t n_layers, int32_t batch,
@@ -176,7 +180,10 @@ typedef struct {
   /* Fused Ulysses "out" exchange over NVLink peer memory (top-1 mode only): when out_peer_count > 0, `out` is
    * ignored and the output row of token tok is stored into out_peer_ptrs[tok / out_peer_rows] at local token
    * tok % out_peer_rows, using out_stride as the strides of ONE peer buffer.  The pointers are peer-mapped device
-   * addresses of every rank's receive buffer (this rank's own included). */
+   * addresses of every rank's receive buffer (this rank's own included).  out_peer_rows * out_peer_count must equal the
+   * number of video tokens; with a text segment (HunyuanVideo) each buffer has text_len more rows behind its
+   * out_peer_rows video rows, and the row of text token j is stored into row out_peer_rows + j of EVERY peer (the head
+   * all-gather of hunyuan.py:186-187); rows of padded text queries are not written — the owner zeroes them. */
   void* out_peer_ptrs[8];
   int32_t out_peer_count;
   int32_t out_peer_rows;

@@ -249,9 +249,15 @@ def sliding_tile_attention(q, k, v, latent_shape, window, tile, text_len: int = 
 # ----------------------------------------------------------------------------------------------------------
 # router and routing — vorta/patch/router.py:33-43; wan.py:396-400
 # ----------------------------------------------------------------------------------------------------------
-def router_forward(temb: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, heads: int) -> torch.Tensor:
-    logits = F.linear(F.silu(temb), weight, bias)
-    return torch.softmax(logits.unflatten(1, (heads, 3)), dim=-1)
+def router_forward(temb: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, heads: int,
+                   module_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """router.py:41-43.  ``module_dtype=torch.bfloat16`` restates what torch does when the router runs in bf16 (the
+    reference's inference default): every module computes in fp32 and rounds its OUTPUT to bf16 — SiLU, Linear (one
+    rounding after the fp32 accumulate + bias), Softmax."""
+    def rnd(t):
+        return t if module_dtype is None else t.to(module_dtype).to(torch.float32)
+    logits = rnd(F.linear(rnd(F.silu(temb.float())), weight.float(), bias.float()))
+    return rnd(torch.softmax(logits.unflatten(1, (heads, 3)), dim=-1))
 
 
 def route_top1(routing_score: torch.Tensor, tau: Optional[float]) -> torch.Tensor:

@@ -110,6 +110,8 @@ def test_hunyuan_fused_prologue_equals_eager_steps():
     rope = (c.cuda(), s.cuda())
     for dual in (True, False):
         attn = FX.FakeHunyuanAttn(H, dual=dual, seed=11).to("cuda", torch.bfloat16)
+        assert proc._qkv_fused(attn, FX.det_tensor((1, S, H * 128), 12).to("cuda", torch.bfloat16),
+                               FX.det_tensor((1, T, H * 128), 13).to("cuda", torch.bfloat16), rope) is None   # grad mode
         hs = FX.det_tensor((1, S, H * 128), 12).to("cuda", torch.bfloat16)
         ehs = FX.det_tensor((1, T, H * 128), 13).to("cuda", torch.bfloat16)
         with torch.no_grad():

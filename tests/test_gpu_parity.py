@@ -179,9 +179,20 @@ def test_router_scores_and_decisions(golden):
     for rec in golden("router.pt"):
         for dt in (torch.float32, torch.bfloat16):
             w, b, temb = rec["weight"].to(dev(), dt), rec["bias"].to(dev(), dt), rec["temb"].to(dev(), dt)
-            ref = O.router_forward(temb.float().cpu(), w.float().cpu(), b.float().cpu(), rec["H"])
+            bf16 = dt == torch.bfloat16
+            ref = O.router_forward(temb.float().cpu(), w.float().cpu(), b.float().cpu(), rec["H"],
+                                   module_dtype=torch.bfloat16 if bf16 else None)
             for tau in (None, 0.0, 0.3, 0.36, 0.4, 0.5):
                 scores, branch = ops.router_forward(temb, w, b, rec["H"], tau)
+                if bf16:
+                    # bf16 routers round after SiLU / Linear / Softmax like torch's bf16 modules: bf16-exact scores
+                    # within one ulp of the restatement (accumulation order), decisions exact on the kernel's scores
+                    got = scores[0].cpu()
+                    assert torch.equal(got, got.to(torch.bfloat16).float())
+                    assert bool(((got - ref).abs() <= ref.abs() * 2.0 ** -7).all())
+                    tau_r = None if tau is None else float(torch.tensor(tau).to(torch.bfloat16))
+                    assert torch.equal(branch[0].cpu(), O.route_top1(got, tau_r).to(torch.int32))
+                    continue
                 assert torch.allclose(scores[0].cpu(), ref, atol=2e-6, rtol=1e-5)
                 assert torch.equal(branch[0].cpu(), O.route_top1(ref, tau).to(torch.int32))   # bit-exact decisions
                 if dt == torch.float32 and tau is not None:
@@ -407,7 +418,8 @@ def test_hunyuan_processors_vs_reference(golden, kind):
     mix = torch.tensor(FX.MIX, device=dev())
     ev = HunyuanVideoFlashAttnProcessorTripleEval(check_input=True)
     tr = HunyuanVideoFlashAttnProcessorTripleTrain(check_input=True)
-    q, k, v = ev._qkv(attn, hs, ehs, rope)
+    with torch.no_grad():       # the forward-only fused prologue, i.e. the q / k / v the Eval processor itself uses
+        q, k, v = ev._qkv(attn, hs, ehs, rope)
     for got, name in ((q, "q"), (k, "k"), (v, "v")):
         assert_attn_close(got, rec[name], cos_min=0.9999, max_abs=0.08)
 
@@ -738,3 +750,60 @@ def test_out_heads_places_local_heads_in_a_wider_output():
     assert torch.equal(out[:, mine], ref[:, mine])
     rest = [h for h in range(H_all) if h not in mine]
     assert out[:, rest].abs().max().item() == 0
+
+
+def test_bf16_router_matches_reference_router_in_bf16():
+    """The reference's inference default is a bf16 router (scripts/wan/inference.py:132).  Its own ``Router`` module
+    (vorta/patch/router.py, imported from the staged reference files) run in bf16 on the GPU against the kernel's bf16
+    mode: scores within one bf16 ulp (the GEMV accumulation order differs), and the top-1 / threshold decision identical
+    for every head whose two best reference scores are more than one ulp apart (closer ones are ties either way)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference files not staged (oracle/stage_ref.py)")
+    RefRouter = ref_loader.load().router.Router
+    torch.manual_seed(7)
+    strict = total = 0
+    for E, H, B in ((1536, 12, 2), (5120, 40, 1), (3072, 24, 1)):
+        ref = RefRouter(E, H, 3).to(dev(), torch.bfloat16)
+        mine = Router(E, H).to(dev(), torch.bfloat16)
+        mine.load_state_dict(ref.state_dict())
+        temb = torch.randn((B, E), device=dev()).to(torch.bfloat16)
+        with torch.no_grad():
+            want = ref(temb)                                          # (B, H, 3) bf16
+        got, _ = ops.router_forward(temb, mine.linear.weight, mine.linear.bias, H)
+        got = got[0]
+        assert torch.equal(got, got.to(torch.bfloat16).float())      # bf16-exact values in the fp32 buffer
+        ulp = want.float().abs() * 2.0 ** -7
+        assert bool(((got - want.float()).abs() <= ulp).all())
+        for tau in (0.3, 0.36):
+            _, branch = ops.router_forward(temb, mine.linear.weight, mine.linear.bias, H, tau)
+            s, idx = want[0].topk(1, dim=-1)                          # wan.py:398-400 on the bf16 scores
+            idx = idx.clone()
+            idx[s < tau] = 0
+            top2 = want[0].float().topk(2, dim=-1).values
+            clear = ((top2[:, 0] - top2[:, 1]) > 2 * ulp[0].max(dim=-1).values) & \
+                    ((top2[:, 0] - tau).abs() > 2 * ulp[0].max(dim=-1).values)
+            assert torch.equal(branch[0][clear].cpu(), idx.squeeze(-1)[clear].to(torch.int32).cpu())
+            strict += int(clear.sum())
+            total += H
+    assert strict > 0.5 * total
+
+
+def test_sliding_direct_raster_loads(monkeypatch):
+    """Opt-in path (VB_ATTN_SLIDING_DIRECT=1): sliding heads fetch tile-major blocks straight from the raster tensors
+    through a 5-D tensor map (one w-row box per TMA operation) instead of reading a tile-major copy.  Must give the
+    same bits as the default path: same kernel order, same arithmetic, only the loads differ.  Tile widths 16, 8 and 4
+    (sub-atom boxes of SWIZZLE_128B) and a text tail (linear rows behind the grid rows)."""
+    for lat, tile, lw, tl, tv in (((6, 18, 32), (3, 9, 16), (3, 3, 2), 0, 0), ((6, 18, 16), (3, 9, 8), (3, 3, 2), 0, 0),
+                                  ((10, 12, 16), (5, 6, 4), (2, 3, 2), 0, 0), ((6, 12, 8), (3, 6, 4), (2, 3, 2), 40, 23)):
+        plan = ops.Plan(lat, tile, (3, 3, 3), lw, 0.5, text_len=tl, text_valid=tv)
+        S, H = plan.seq_len, 3
+        g = torch.Generator().manual_seed(S)
+        q, k, v = (torch.randn((1, S + tl, H, 128), generator=g).to(torch.bfloat16).to(dev()).transpose(1, 2)
+                   for _ in range(3))
+        monkeypatch.delenv("VB_ATTN_SLIDING_DIRECT", raising=False)
+        want = ops.routed_attention(plan, q, k, v, branch=[2, 0, 2])
+        monkeypatch.setenv("VB_ATTN_SLIDING_DIRECT", "1")
+        got = ops.routed_attention(plan, q, k, v, branch=[2, 0, 2])
+        monkeypatch.delenv("VB_ATTN_SLIDING_DIRECT", raising=False)
+        assert torch.equal(got, want)

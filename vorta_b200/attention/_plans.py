@@ -31,14 +31,17 @@ def get_plan(latent_shape, tile_size, window_size, lowres_window, n_unpooled: in
              text_valid: int = 0) -> ops.Plan:
     # the plan's device tables live on the device that is current when it is created
     dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
-    key = (_t3(latent_shape), _t3(tile_size), _t3(window_size), _t3(lowres_window), int(n_unpooled), int(text_len), dev)
+    # text_valid is part of the key: prompts of different length (true CFG alternates two) each keep their own
+    # schedule tables instead of rebuilding one plan with a device synchronize on every switch
+    key = (_t3(latent_shape), _t3(tile_size), _t3(window_size), _t3(lowres_window), int(n_unpooled), int(text_len),
+           int(text_valid), dev)
     plan = _CACHE.get(key)
     if plan is None:
+        if len(_CACHE) >= 64:                      # bounded: drop the oldest geometry
+            _CACHE.pop(next(iter(_CACHE)))
         plan = ops.Plan(key[0], key[1], key[2], key[3], n_unpooled=int(n_unpooled), text_len=int(text_len),
                         text_valid=int(text_valid))
         _CACHE[key] = plan
-    elif plan.text_valid != int(text_valid):
-        plan.set_text_valid(int(text_valid))
     return plan
 
 

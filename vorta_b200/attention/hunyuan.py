@@ -15,6 +15,7 @@ import torch
 from .. import _lib as L
 from .. import ops
 from ..ulysses import SP_STATE, all_gather, balance, exchange_out, exchange_qkv, local_heads, shrink_dim
+from ..ulysses.peer import get_exchange
 from ._plans import get_plan, infer_lowres_window
 from .coreset_select import LowresGroupInfo
 from .wan import _top1_branches
@@ -132,6 +133,20 @@ class HunyuanVideoFlashAttnProcessor:
             hp = H // P
             if branch is not None and balance.enabled():      # cost-balanced head placement
                 head_at = balance.balance_heads(list(branch), balance.branch_costs(plan), P)
+            ex = get_exchange(H, query.shape[2] - text_len, query.device, text_len) if weights is None else None
+            if ex is not None:
+                # NVLink peer-memory path (top-1 routing): video rows of Q / K / V are stored straight into the head
+                # owners' buffers, this rank's heads of the replicated text rows are copied locally, and the attention
+                # epilogue stores video rows to the token owner and text rows to every rank
+                parts = [(t[:, :, :-text_len], t[:, :, -text_len:]) for t in (query, key, value)]
+                q, k, v = ex.scatter_qkv(*[p_[0] for p_ in parts], head_at, text=[p_[1] for p_ in parts])
+                ex.zero_padded_text(plan.text_valid)
+                mine = list(head_at[r * hp:(r + 1) * hp]) if head_at is not None else list(range(r * hp, (r + 1) * hp))
+                ops.routed_attention(plan, q, k, v, branch=local_heads(list(branch), H, head_at), flags=flags,
+                                     out_peers=ex.out_ptrs, out_peer_rows=ex.s_loc, out_peer_strides=(0, 128, H * 128),
+                                     out_heads=mine)
+                out = ex.finish_out()
+                return out[:, :, :-text_len], out[:, :, -text_len:]
             qv, kv, vv = exchange_qkv(query[:, :, :-text_len], key[:, :, :-text_len], value[:, :, :-text_len],
                                       extra_rows=text_len, head_at=head_at)
             mine = None
@@ -158,12 +173,14 @@ class HunyuanVideoFlashAttnProcessor:
         return video, text
 
     def _step_attention(self, query, key, value, attention_mask, encoder_hidden_states_seq_len: int,
-                        skip_communication: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                        skip_communication: bool = False, text_valid: Optional[int] = None
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Full attention over the first S + valid_text tokens, zeros for padded text rows (hunyuan.py:136-189)."""
         text_len = encoder_hidden_states_seq_len
         video_len = (query.shape[2] - text_len) * (SP_STATE.sp_size if SP_STATE.enabled and not skip_communication else 1)
-        plan = get_plan((1, 1, video_len), (1, 1, video_len), (1, 1, 1), (1, 1, 1), 0, text_len,
-                        _valid_text(attention_mask, video_len))
+        if text_valid is None:
+            text_valid = _valid_text(attention_mask, video_len)
+        plan = get_plan((1, 1, video_len), (1, 1, video_len), (1, 1, 1), (1, 1, 1), 0, text_len, text_valid)
         H = query.shape[1]
         return self._joint_attention(query, key, value, plan, text_len, branch=[L.BRANCH_FULL] * H)
 
@@ -183,8 +200,10 @@ class HunyuanVideoFlashAttnProcessor:
         the rows in the joint [video | text] tensor; V is written into it by the GEMM itself.  None = not applicable
         (other norm modules, dtypes, devices): the eager steps run instead."""
         norms = [_head_norm(getattr(attn, n, None)) for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k")]
+        wants_grad = torch.is_grad_enabled() and (hidden_states.requires_grad or encoder_hidden_states.requires_grad
+                                                  or attn.to_q.weight.requires_grad)
         if (hidden_states.dtype != torch.bfloat16 or not hidden_states.is_cuda or hidden_states.dim() != 3
-                or any(n is False for n in norms) or torch.is_grad_enabled() and hidden_states.requires_grad):
+                or any(n is False for n in norms) or wants_grad):      # the fused kernels are forward-only
             return None
         (wq, eq_), (wk, ek_), (waq, eaq), (wak, eak) = norms
         B, S, _ = hidden_states.shape
@@ -221,11 +240,13 @@ class HunyuanVideoFlashAttnProcessor:
         query, key = self._step_rotary_emb(attn, query, key, encoder_hidden_states.shape[1], image_rotary_emb)
         return self._step_encoder_to_qkv_and_concat(attn, query, key, value, encoder_hidden_states)
 
-    def __call__(self, attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb
-                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    def __call__(self, attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb,
+                 text_valid: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``text_valid`` (extra, optional): the number of un-padded text tokens when the caller already knows it —
+        the reference reads it from ``attention_mask`` with a host sync in every layer (hunyuan.py:169)."""
         query, key, value = self._qkv(attn, hidden_states, encoder_hidden_states, image_rotary_emb)
         hidden_states, encoder_hidden_states = self._step_attention(
-            query, key, value, attention_mask, encoder_hidden_states.shape[1])
+            query, key, value, attention_mask, encoder_hidden_states.shape[1], text_valid=text_valid)
         return self._step_to_output(attn, hidden_states, encoder_hidden_states)
 
 
@@ -250,18 +271,21 @@ class HunyuanVideoFlashAttnProcessorTripleTrain(HunyuanVideoFlashAttnProcessor):
                 raise ValueError(f"Input sequence length {seq_length} does not match low-res info "
                                  f"{num_groups}x{group_size}.")
 
-    def _plan(self, lowres_group_info, window_size, tile_size, latent_shape, text_len, attention_mask) -> ops.Plan:
+    def _plan(self, lowres_group_info, window_size, tile_size, latent_shape, text_len, attention_mask,
+              text_valid: Optional[int] = None) -> ops.Plan:
         S = latent_shape[0] * latent_shape[1] * latent_shape[2]
         lowres_window = infer_lowres_window(lowres_group_info, latent_shape)
+        if text_valid is None:
+            text_valid = _valid_text(attention_mask, S)
         return get_plan(latent_shape, tile_size, window_size, lowres_window,
-                        lowres_group_info.num_unpooled_tokens_per_group, text_len, _valid_text(attention_mask, S))
+                        lowres_group_info.num_unpooled_tokens_per_group, text_len, text_valid)
 
     def _routed(self, attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb, lowres_group_info,
-                window_size, tile_size, latent_shape, branch=None, weights=None):
+                window_size, tile_size, latent_shape, branch=None, weights=None, text_valid=None):
         self._check_input(hidden_states, lowres_group_info, latent_shape, window_size, tile_size)
         text_len = encoder_hidden_states.shape[1]
         query, key, value = self._qkv(attn, hidden_states, encoder_hidden_states, image_rotary_emb)
-        plan = self._plan(lowres_group_info, window_size, tile_size, latent_shape, text_len, attention_mask)
+        plan = self._plan(lowres_group_info, window_size, tile_size, latent_shape, text_len, attention_mask, text_valid)
         # K and V are pooled with K's own matching, the output is unpooled with Q's (hunyuan.py:433-451)
         video, text = self._joint_attention(query, key, value, plan, text_len, branch=branch, weights=weights,
                                             flags=L.ATTN_CORESET_KV_FROM_K)
@@ -271,12 +295,14 @@ class HunyuanVideoFlashAttnProcessorTripleTrain(HunyuanVideoFlashAttnProcessor):
                  use_original_attn: bool = False, routing_score: Optional[torch.Tensor] = None,
                  lowres_group_info: Optional[LowresGroupInfo] = None, flex_attn_mask_func: Optional[Callable] = None,
                  window_size: Tuple[int, int, int] = (3, 3, 3), tile_size: Tuple[int, int, int] = (6, 8, 8),
-                 latent_shape: Tuple[int, int, int] = (30, 48, 80)) -> Tuple[torch.Tensor, torch.Tensor]:
+                 latent_shape: Tuple[int, int, int] = (30, 48, 80), text_valid: Optional[int] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
         if use_original_attn:
             return HunyuanVideoFlashAttnProcessor.__call__(self, attn, hidden_states, encoder_hidden_states,
-                                                           attention_mask, image_rotary_emb)
+                                                           attention_mask, image_rotary_emb, text_valid=text_valid)
         return self._routed(attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb,
-                            lowres_group_info, window_size, tile_size, latent_shape, weights=routing_score)
+                            lowres_group_info, window_size, tile_size, latent_shape, weights=routing_score,
+                            text_valid=text_valid)
 
 
 class HunyuanVideoFlashAttnProcessorTripleEval(HunyuanVideoFlashAttnProcessorTripleTrain):
@@ -285,8 +311,10 @@ class HunyuanVideoFlashAttnProcessorTripleEval(HunyuanVideoFlashAttnProcessorTri
                  routing_score: torch.Tensor, tau_sparse: float, lowres_group_info: Optional[LowresGroupInfo] = None,
                  flex_attn_mask_func: Optional[Callable] = None, window_size: Tuple[int, int, int] = (3, 3, 3),
                  tile_size: Tuple[int, int, int] = (6, 8, 8), latent_shape: Tuple[int, int, int] = (30, 48, 80),
-                 branch: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                 branch: Optional[Sequence[int]] = None, text_valid: Optional[int] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
         if branch is None:
             branch = _top1_branches(routing_score, tau_sparse)          # hunyuan.py:620-624
         return self._routed(attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb,
-                            lowres_group_info, window_size, tile_size, latent_shape, branch=branch)
+                            lowres_group_info, window_size, tile_size, latent_shape, branch=branch,
+                            text_valid=text_valid)

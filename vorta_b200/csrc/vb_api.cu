@@ -70,6 +70,8 @@ int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, cons
                                int world, int rank, const int32_t* head_at, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
+int make_grid_tensor_map(CUtensorMap* map, const void* base, const int32_t* latent, int32_t tile_w, int64_t heads,
+                         int64_t stride_h, int64_t stride_s);
 int launch_attn(const AttnTmaps& tmaps, const AttnParams& params, int n_ctas, cudaStream_t stream);
 
 
@@ -256,10 +258,12 @@ static int build_text_dependent(vb_plan* pl) {
         pl->sliding.add_query_range(tile_id * tau, tau, run_begin, run_count, keys);
         if (tile_id == 0) pl->keys_per_query = keys - tv;
       }
-  if (tv > 0) {   // valid text queries see every non-pad key (:108)
+  if (tv > 0) {   // valid text queries see every non-pad key (:108); two runs, so that no 128-key block straddles the
+                  // video / text boundary (video rows come through the raster-grid tensor map, text rows through the linear one)
     const int run_begin = static_cast<int>(pl->sliding.runs.size());
-    pl->sliding.runs.push_back({0, S + tv});
-    pl->sliding.add_query_range(S, tv, run_begin, 1, S + tv);
+    pl->sliding.runs.push_back({0, S});
+    pl->sliding.runs.push_back({S, tv});
+    pl->sliding.add_query_range(S, tv, run_begin, 2, S + tv);
   }
   pl->full.finalize();
   pl->coreset.finalize();
@@ -571,6 +575,7 @@ struct BranchLaunch {
   const int32_t* bcast_map;
   int64_t bcast_stride_b, bcast_stride_h;
   int32_t bcast_rows, bcast_n;
+  const vb_plan* grid_plan;      // non-null: q, k, v are the caller's raster tensors, rows are tile-major (AttnSeg::grid_rows)
 };
 }  // namespace
 
@@ -611,6 +616,20 @@ static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_
     s.out_map = bl.out_map; s.out_map_stride_b = bl.out_map_stride_b; s.out_map_stride_h = bl.out_map_stride_h;
     s.bcast_map = bl.bcast_map; s.bcast_stride_b = bl.bcast_stride_b; s.bcast_stride_h = bl.bcast_stride_h;
     s.bcast_rows = bl.bcast_rows; s.bcast_n = bl.bcast_n;
+    if (bl.grid_plan != nullptr) {
+      const vb_plan* gp = bl.grid_plan;
+      const void* base[3] = {bl.q, bl.k, bl.v};
+      const int64_t* st[3] = {bl.qs, bl.ks, bl.vs};
+      for (int t = 0; t < 3; ++t)
+        if ((rc = make_grid_tensor_map(&tm.grid[t], base[t], gp->d.latent, gp->d.tile[2], bl.n_heads_tensor, st[t][1],
+                                       st[t][2])))
+          return rc;
+      s.grid_rows = gp->S;
+      for (int d = 0; d < 3; ++d) {
+        s.tile[d] = gp->d.tile[d];
+        s.ntile[d] = gp->nt[d];
+      }
+    }
     s.n_pairs = static_cast<int32_t>(bl.sched->pairs.size());
     s.n_heads = static_cast<int32_t>(sg.heads.size());
     s.head0 = head0;
@@ -675,8 +694,10 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   const vb_attn_args& a = *args;
   VB_REQUIRE(a.q && a.k && a.v && (a.out || a.out_peer_count > 0), VB_ERR_INVALID, "null tensor");
   VB_REQUIRE(a.out_peer_count >= 0 && a.out_peer_count <= 8, VB_ERR_INVALID, "out_peer_count must be within [0, 8]");
-  VB_REQUIRE(a.out_peer_count == 0 || (a.weights == nullptr && a.out_peer_rows > 0 && pl->d.text_len == 0),
-             VB_ERR_UNSUPPORTED, "peer output needs top-1 routing, out_peer_rows > 0 and no text segment");
+  VB_REQUIRE(a.out_peer_count == 0 ||
+                 (a.weights == nullptr && a.out_peer_rows > 0 &&
+                  static_cast<int64_t>(a.out_peer_rows) * a.out_peer_count == pl->S),
+             VB_ERR_UNSUPPORTED, "peer output needs top-1 routing and out_peer_rows * out_peer_count == video tokens");
   VB_REQUIRE(a.batch > 0 && a.heads > 0, VB_ERR_INVALID, "batch and heads must be positive");
   VB_REQUIRE(a.weights != nullptr || a.branch != nullptr, VB_ERR_INVALID, "need branch ids or blend weights");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -837,39 +858,65 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
 
   // ---------------- branch 2: sliding tile ----------------
   if (!by_branch[2].empty()) {
-    NvtxRange nvtx("vb: sliding tile-major layout");
     const std::vector<int32_t>& hs = by_branch[2];
     const int nh = static_cast<int>(hs.size());
-    const int64_t rows = N;
-    const int64_t bh = static_cast<int64_t>(a.batch) * nh;
-    __nv_bfloat16* tq = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
-    __nv_bfloat16* tk = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
-    __nv_bfloat16* tv = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
-    HeadList heads_s;
-    if ((rc = head_list_of(hs, &heads_s)) != VB_OK) return rc;
-    VB_REQUIRE(tq && tk && tv, VB_ERR_INVALID, "workspace exhausted");
-    GatherParams gp;
-    memset(&gp, 0, sizeof(gp));
-    gp.n_tensors = 3; gp.map = pl->d_tile_map; gp.map_stride_b = 0; gp.map_stride_h = 0;
-    gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = tq;
-    gp.src[1] = static_cast<const __nv_bfloat16*>(a.k); gp.dst[1] = tk;
-    gp.src[2] = static_cast<const __nv_bfloat16*>(a.v); gp.dst[2] = tv;
-    for (int i = 0; i < 3; ++i) {
-      gp.src_stride[0][i] = a.q_stride[i]; gp.src_stride[1][i] = a.k_stride[i]; gp.src_stride[2][i] = a.v_stride[i];
+    // Direct path (opt-in, VB_ATTN_SLIDING_DIRECT=1): the kernel fetches tile-major blocks from the caller's raster
+    // tensors through a 5-D tensor map, one w-row box per TMA operation, so no tile-major copy is written.  Correct
+    // (tests/test_gpu_parity.py::test_sliding_direct_raster_loads) but NOT the default: a 128-row block becomes
+    // 2 * 128 / tile_w boxes of tile_w x 128 B, and the TMA unit is bound by the box count, not the bytes — Wan-14B
+    // (tile_w 16, 16 boxes of 2 KB per block) 753 vs 1127 TFLOP/s with the layout pass (1050 including it), Wan-1.3B
+    // (tile_w 4, 64 boxes of 512 B) 182 vs 655 (profiles/r2e_perf_*.log).  The same measurement rules out
+    // tile::gather4 row gathers for the coreset branch (64 operations of 512 B per block; the instruction itself works,
+    // tests/micro/gather4_probe.cu).  The layout pass costs ~0.5 % of a Wan-14B step.
+    const int tw = pl->d.tile[2];
+    const char* direct_env = getenv("VB_ATTN_SLIDING_DIRECT");
+    const bool direct = direct_env != nullptr && direct_env[0] == '1' && a.batch == 1 && kBlockN % tw == 0 && tw >= 4;
+    if (direct) {
+      NvtxRange nvtx("vb: sliding tile (raster loads, no layout pass)");
+      BranchLaunch bl;
+      memset(&bl, 0, sizeof(bl));
+      bl.q = static_cast<const __nv_bfloat16*>(a.q);
+      bl.k = static_cast<const __nv_bfloat16*>(a.k);
+      bl.v = static_cast<const __nv_bfloat16*>(a.v);
+      for (int i = 0; i < 3; ++i) { bl.qs[i] = a.q_stride[i]; bl.ks[i] = a.k_stride[i]; bl.vs[i] = a.v_stride[i]; }
+      bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = a.heads;   // linear maps: text rows keep their place
+      bl.sched = &pl->sliding;
+      bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
+      bl.grid_plan = pl;
+      if ((rc = for_batches(bl, hs, 2, false)) != VB_OK) return rc;
+    } else {
+      NvtxRange nvtx("vb: sliding tile-major layout");
+      const int64_t rows = N;
+      const int64_t bh = static_cast<int64_t>(a.batch) * nh;
+      __nv_bfloat16* tq = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+      __nv_bfloat16* tk = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+      __nv_bfloat16* tv = static_cast<__nv_bfloat16*>(ws.take(bh * rows * kHeadDim * 2));
+      HeadList heads_s;
+      if ((rc = head_list_of(hs, &heads_s)) != VB_OK) return rc;
+      VB_REQUIRE(tq && tk && tv, VB_ERR_INVALID, "workspace exhausted");
+      GatherParams gp;
+      memset(&gp, 0, sizeof(gp));
+      gp.n_tensors = 3; gp.map = pl->d_tile_map; gp.map_stride_b = 0; gp.map_stride_h = 0;
+      gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = tq;
+      gp.src[1] = static_cast<const __nv_bfloat16*>(a.k); gp.dst[1] = tk;
+      gp.src[2] = static_cast<const __nv_bfloat16*>(a.v); gp.dst[2] = tv;
+      for (int i = 0; i < 3; ++i) {
+        gp.src_stride[0][i] = a.q_stride[i]; gp.src_stride[1][i] = a.k_stride[i]; gp.src_stride[2][i] = a.v_stride[i];
+      }
+      gp.dst_stride[0] = nh * rows * kHeadDim; gp.dst_stride[1] = rows * kHeadDim; gp.dst_stride[2] = kHeadDim;
+      gp.head_list = heads_s; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
+      if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
+      ++g_launches;
+      BranchLaunch bl;
+      memset(&bl, 0, sizeof(bl));
+      bl.q = tq; bl.k = tk; bl.v = tv;
+      const int64_t st[3] = {nh * rows * kHeadDim, rows * kHeadDim, kHeadDim};
+      for (int i = 0; i < 3; ++i) { bl.qs[i] = st[i]; bl.ks[i] = st[i]; bl.vs[i] = st[i]; }
+      bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = nh;
+      bl.sched = &pl->sliding;
+      bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
+      if ((rc = for_batches(bl, hs, 2, true)) != VB_OK) return rc;
     }
-    gp.dst_stride[0] = nh * rows * kHeadDim; gp.dst_stride[1] = rows * kHeadDim; gp.dst_stride[2] = kHeadDim;
-    gp.head_list = heads_s; gp.batch = a.batch; gp.heads = nh; gp.n_rows = static_cast<int32_t>(rows);
-    if ((rc = launch_gather_rows(gp, stream)) != VB_OK) return rc;
-    ++g_launches;
-    BranchLaunch bl;
-    memset(&bl, 0, sizeof(bl));
-    bl.q = tq; bl.k = tk; bl.v = tv;
-    const int64_t st[3] = {nh * rows * kHeadDim, rows * kHeadDim, kHeadDim};
-    for (int i = 0; i < 3; ++i) { bl.qs[i] = st[i]; bl.ks[i] = st[i]; bl.vs[i] = st[i]; }
-    bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = nh;
-    bl.sched = &pl->sliding;
-    bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
-    if ((rc = for_batches(bl, hs, 2, true)) != VB_OK) return rc;
   }
 
   if (n_deferred > 0) {
@@ -880,7 +927,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   }
 
   // ---------------- padded text queries produce zeros (hunyuan.py:176; flex fully-masked rows) ----------------
-  if (TL > TV) {
+  if (TL > TV && a.out_peer_count == 0) {      // (peer mode: every rank zeroes its own receive buffer)
     rc = launch_zero_rows(static_cast<__nv_bfloat16*>(a.out), a.out_stride[0], a.out_stride[1], a.out_stride[2],
                           a.batch, a.heads, S + TV, TL - TV, stream);
     if (rc != VB_OK) return rc;

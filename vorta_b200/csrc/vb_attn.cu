@@ -205,6 +205,11 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
       tma_prefetch_desc(&tmaps.m[i][0]);
       tma_prefetch_desc(&tmaps.m[i][1]);
       tma_prefetch_desc(&tmaps.m[i][2]);
+      if (p.seg[i].grid_rows > 0) {
+        tma_prefetch_desc(&tmaps.grid[0]);
+        tma_prefetch_desc(&tmaps.grid[1]);
+        tma_prefetch_desc(&tmaps.grid[2]);
+      }
     }
   }
   if (warp == kMmaWarp) {
@@ -226,56 +231,80 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
 
   if (warp == kTmaWarp) {
     // ======================================= TMA producer =======================================
-    if (lane == 0) {
-      uint32_t load_idx = 0;                 // position in the K/V ring, running through all items
-      uint32_t q_uses[2] = {0, 0};           // items that used Q_t so far
-      for (uint32_t n = 0;; ++n) {
-        // fetch and publish: the first item is the CTA index, the rest come from the self-resetting global counter
-        // (atomicInc wraps to 0 on the launch's n_items-th fetch: gridDim.x of the fetches are the "no more work" ones)
-        int item = static_cast<int>(blockIdx.x);
-        if (n > 0) item = static_cast<int>(gridDim.x + atomicInc(p.work_counter, static_cast<unsigned>(p.n_items - 1)));
-        if (item >= p.n_items) item = -1;
-        mbar_wait(&sm.bar_item_empty[n & 1u], ((n >> 1) & 1u) ^ 1u);
+    // The whole warp runs the loop converged (one lane would do for linear rows; the raster path below issues one box
+    // per lane).  Lane 0 owns the work counter, every expect_tx arrive and the linear loads.
+    uint32_t load_idx = 0;                 // position in the K/V ring, running through all items
+    uint32_t q_uses[2] = {0, 0};           // items that used Q_t so far
+    for (uint32_t n = 0;; ++n) {
+      // fetch and publish: the first item is the CTA index, the rest come from the self-resetting global counter
+      // (atomicInc wraps to 0 on the launch's n_items-th fetch: gridDim.x of the fetches are the "no more work" ones)
+      int item = static_cast<int>(blockIdx.x);
+      if (n > 0) {
+        if (lane == 0) item = static_cast<int>(gridDim.x + atomicInc(p.work_counter, static_cast<unsigned>(p.n_items - 1)));
+        item = __shfl_sync(0xffffffffu, item, 0);
+      }
+      if (item >= p.n_items) item = -1;
+      mbar_wait(&sm.bar_item_empty[n & 1u], ((n >> 1) & 1u) ^ 1u);
+      if (lane == 0) {
         *reinterpret_cast<volatile int32_t*>(&sm.item_idx[n & 1u]) = item;
         mbar_arrive(&sm.bar_item_full[n & 1u]);          // release semantics: the store above is visible to the waiters
-        if (item < 0) break;
-        const Item it = decode_item(p, item);
-        const AttnSeg& seg = p.seg[it.seg_idx];
-        const CUtensorMap* tmap_q = &tmaps.m[it.seg_idx][0];
-        const CUtensorMap* tmap_k = &tmaps.m[it.seg_idx][1];
-        const CUtensorMap* tmap_v = &tmaps.m[it.seg_idx][2];
-        const int nq = it.pair.nq, hk = it.head.hk, batch = it.batch;
-        auto load_kv = [&](const CUtensorMap* m, int row0) {
-          const uint32_t slot = load_idx % kNumSlots;
-          const uint32_t phase = (load_idx / kNumSlots) & 1u;
-          mbar_wait(&bar_slot_empty[slot], phase ^ 1u);
-          mbar_arrive_expect_tx(&bar_slot_full[slot], kTileBytes);
-          uint8_t* dst = smem_kv + slot * kTileBytes;
-          tma_load_4d(dst, m, &bar_slot_full[slot], 0, row0, hk, batch);
-          tma_load_4d(dst + kHalfBytes, m, &bar_slot_full[slot], 64, row0, hk, batch);
-          ++load_idx;
-        };
-        auto load_q = [&]() {
-          for (int t = 0; t < nq; ++t) {
-            if (q_uses[t] > 0) mbar_wait(&sm.bar_q_empty[t], (q_uses[t] - 1) & 1u);
-            ++q_uses[t];
-            mbar_arrive_expect_tx(&bar_q_full[t], kTileBytes);
-            tma_load_4d(smem_q + t * kTileBytes, tmap_q, &bar_q_full[t], 0, it.pair.q_row0[t], hk, batch);
-            tma_load_4d(smem_q + t * kTileBytes + kHalfBytes, tmap_q, &bar_q_full[t], 64, it.pair.q_row0[t], hk, batch);
+      }
+      if (item < 0) break;
+      const Item it = decode_item(p, item);
+      const AttnSeg& seg = p.seg[it.seg_idx];
+      const CUtensorMap* tmap_q = &tmaps.m[it.seg_idx][0];
+      const CUtensorMap* tmap_k = &tmaps.m[it.seg_idx][1];
+      const CUtensorMap* tmap_v = &tmaps.m[it.seg_idx][2];
+      const int nq = it.pair.nq, hk = it.head.hk, batch = it.batch;
+      // 128 rows [row0, row0 + 128) of one operand -> dst (two 64-channel halves of 16 KB), completion on bar
+      auto load_rows = [&](const CUtensorMap* lin, int which, int row0, uint8_t* dst, uint64_t* bar) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, kTileBytes);
+        __syncwarp();
+        if (seg.grid_rows > 0 && row0 < seg.grid_rows) {
+          // tile-major rows of the raster grid: one (64 channels x tile_w tokens) box per w-row and channel half;
+          // rows behind the last tile have t >= T and are zero-filled by the TMA unit (the bytes still count)
+          const CUtensorMap* gm = &tmaps.grid[which];
+          const int tw = seg.tile[2], thw = seg.tile[1] * tw, tau = seg.tile[0] * thw;
+          const int n12 = seg.ntile[1] * seg.ntile[2];
+          for (int i = lane; i < 2 * (kBlockN / tw); i += 32) {
+            const int box = i >> 1, half = i & 1;
+            const int r = row0 + box * tw;
+            const int tile = r / tau, intra = r - tile * tau;
+            const int it_ = intra / thw, rem = intra - it_ * thw, ih = rem / tw, iw = rem - ih * tw;
+            const int ta = tile / n12, tr = tile - ta * n12, tb_ = tr / seg.ntile[2], tc = tr - tb_ * seg.ntile[2];
+            tma_load_5d(dst + half * kHalfBytes + box * tw * 128, gm, bar, half * 64, tc * tw + iw,
+                        tb_ * seg.tile[1] + ih, ta * seg.tile[0] + it_, hk);
           }
-        };
-        BlockWalker w0(seg.runs + it.pair.run_begin, it.pair.run_count);
-        BlockWalker w1(seg.runs + it.pair.run_begin2, it.pair.split ? it.pair.run_count2 : 0);
-        int row0, valid;
-        // the first K block does not depend on the previous item having released Q: request it first
-        for (int j = 0; w0.next(row0, valid); ++j) {
-          load_kv(tmap_k, row0);
-          if (j == 0) load_q();
-          load_kv(tmap_v, row0);
-          if (it.pair.split && w1.next(row0, valid)) {      // K1 V1 of the same block step
-            load_kv(tmap_k, row0);
-            load_kv(tmap_v, row0);
-          }
+        } else if (lane == 0) {
+          tma_load_4d(dst, lin, bar, 0, row0, hk, batch);
+          tma_load_4d(dst + kHalfBytes, lin, bar, 64, row0, hk, batch);
+        }
+      };
+      auto load_kv = [&](const CUtensorMap* m, int which, int row0) {
+        const uint32_t slot = load_idx % kNumSlots;
+        const uint32_t phase = (load_idx / kNumSlots) & 1u;
+        mbar_wait(&bar_slot_empty[slot], phase ^ 1u);
+        load_rows(m, which, row0, smem_kv + slot * kTileBytes, &bar_slot_full[slot]);
+        ++load_idx;
+      };
+      auto load_q = [&]() {
+        for (int t = 0; t < nq; ++t) {
+          if (q_uses[t] > 0) mbar_wait(&sm.bar_q_empty[t], (q_uses[t] - 1) & 1u);
+          ++q_uses[t];
+          load_rows(tmap_q, 0, it.pair.q_row0[t], smem_q + t * kTileBytes, &bar_q_full[t]);
+        }
+      };
+      BlockWalker w0(seg.runs + it.pair.run_begin, it.pair.run_count);
+      BlockWalker w1(seg.runs + it.pair.run_begin2, it.pair.split ? it.pair.run_count2 : 0);
+      int row0, valid;
+      // the first K block does not depend on the previous item having released Q: request it first
+      for (int j = 0; w0.next(row0, valid); ++j) {
+        load_kv(tmap_k, 1, row0);
+        if (j == 0) load_q();
+        load_kv(tmap_v, 2, row0);
+        if (it.pair.split && w1.next(row0, valid)) {      // K1 V1 of the same block step
+          load_kv(tmap_k, 1, row0);
+          load_kv(tmap_v, 2, row0);
         }
       }
     }
@@ -585,33 +614,45 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
         }
         for (int dsti = 0; dsti < n_dst; ++dsti) {
           int64_t tok = dsti == 0 ? dst_tok : static_cast<int64_t>(bc[dsti - 1]);
-          __nv_bfloat16* obase = p.out;
-          if (p.out_peer_count > 0) {      // fused Ulysses "out" exchange: the owner rank of this token gets the row
-            const int peer = static_cast<int>(tok / p.out_peer_rows);
-            obase = p.out_peers[peer];
-            tok -= static_cast<int64_t>(peer) * p.out_peer_rows;
-          }
-          uint4* dst = reinterpret_cast<uint4*>(obase + head_off + tok * p.out_stride_s + c * 32);
-#pragma unroll
-          for (int q4i = 0; q4i < 4; ++q4i) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q4i * 8 + i]) * inv;
-            if (accumulate) {
-              const uint4 prev = dst[q4i];
-              const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                f[2 * i + 0] += __uint_as_float(pw[i] << 16);
-                f[2 * i + 1] += __uint_as_float(pw[i] & 0xffff0000u);
-              }
+          // fused Ulysses "out" exchange: a video token's row goes to the rank that owns the token; a text row (tokens
+          // behind the out_peer_count * out_peer_rows video tokens; HunyuanVideo) goes to EVERY rank, behind its video
+          // rows — the all-gather over heads of hunyuan.py:186-187 as plain NVLink stores
+          int pe = 0, pe_end = 1;
+          if (p.out_peer_count > 0) {
+            const int64_t video_rows = static_cast<int64_t>(p.out_peer_count) * p.out_peer_rows;
+            if (tok < video_rows) {
+              pe = static_cast<int>(tok / p.out_peer_rows);
+              pe_end = pe + 1;
+              tok -= static_cast<int64_t>(pe) * p.out_peer_rows;
+            } else {
+              pe_end = p.out_peer_count;
+              tok = p.out_peer_rows + (tok - video_rows);
             }
-            uint4 v;
-            v.x = pack_bf16x2(f[0], f[1]);
-            v.y = pack_bf16x2(f[2], f[3]);
-            v.z = pack_bf16x2(f[4], f[5]);
-            v.w = pack_bf16x2(f[6], f[7]);
-            dst[q4i] = v;
+          }
+          for (; pe < pe_end; ++pe) {
+            __nv_bfloat16* obase = p.out_peer_count > 0 ? p.out_peers[pe] : p.out;
+            uint4* dst = reinterpret_cast<uint4*>(obase + head_off + tok * p.out_stride_s + c * 32);
+#pragma unroll
+            for (int q4i = 0; q4i < 4; ++q4i) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q4i * 8 + i]) * inv;
+              if (accumulate) {
+                const uint4 prev = dst[q4i];
+                const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[2 * i + 0] += __uint_as_float(pw[i] << 16);
+                  f[2 * i + 1] += __uint_as_float(pw[i] & 0xffff0000u);
+                }
+              }
+              uint4 v;
+              v.x = pack_bf16x2(f[0], f[1]);
+              v.y = pack_bf16x2(f[2], f[3]);
+              v.z = pack_bf16x2(f[4], f[5]);
+              v.w = pack_bf16x2(f[6], f[7]);
+              dst[q4i] = v;
+            }
           }
         }
       }
@@ -666,6 +707,28 @@ int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int6
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VB_OK;
+}
+
+// 5-D bf16 tensor map over the raster token grid of ONE batch element: (channel = 128, W, H, T, head) with a
+// (64, tile_w, 1, 1, 1) box, SWIZZLE_128B; token (t, h, w) sits at ((t * H + h) * W + w) * stride_s.
+int make_grid_tensor_map(CUtensorMap* map, const void* base, const int32_t* latent, int32_t tile_w, int64_t heads,
+                         int64_t stride_h, int64_t stride_s) {
+  PFN_encodeTiled enc = get_encode_fn();
+  VB_REQUIRE(enc != nullptr, VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  VB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && stride_s % 8 == 0 && stride_h % 8 == 0, VB_ERR_INVALID,
+             "tensor base and strides must be 16-byte aligned");
+  const int64_t T = latent[0], H = latent[1], W = latent[2];
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(heads)};
+  auto fix = [](int64_t s) { return static_cast<cuuint64_t>((s > 0 ? s : 8) * 2); };
+  cuuint64_t strides[4] = {fix(stride_s), fix(W * stride_s), fix(H * W * stride_s), fix(stride_h)};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(tile_w), 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_CUDA, "cuTensorMapEncodeTiled (5-D grid) failed with CUresult %d", (int)r);
   return VB_OK;
 }
 

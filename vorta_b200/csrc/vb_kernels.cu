@@ -363,6 +363,19 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// bf16 routers (the reference's inference default, scripts/wan/inference.py:132 router_dtype=torch.bfloat16): torch
+// rounds after every module — SiLU output, Linear output (fp32 accumulate, one rounding), Softmax output — and the
+// top-1 / threshold compare then sees bf16 scores.  With bf16 weights the kernel rounds at the same three points, so
+// heads whose fp32 scores are closer than a bf16 ulp tie (-> lowest expert index) exactly like they do there.
+template <typename T>
+struct RoundLike {
+  static __device__ __forceinline__ float r(float v) { return v; }
+};
+template <>
+struct RoundLike<__nv_bfloat16> {
+  static __device__ __forceinline__ float r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+
 template <typename TE, typename TW>
 __global__ void __launch_bounds__(256)
 vb_router_kernel(const TE* temb, const TW* w, const TW* bias, int64_t w_layer_stride, int64_t bias_layer_stride,
@@ -374,7 +387,7 @@ vb_router_kernel(const TE* temb, const TW* w, const TW* bias, int64_t w_layer_st
   const int n_out = heads * 3;
   for (int i = threadIdx.x; i < embed_dim; i += blockDim.x) {
     const float x = to_f32(temb[static_cast<int64_t>(b) * embed_dim + i]);
-    s_act[i] = x / (1.f + expf(-x));   // SiLU
+    s_act[i] = RoundLike<TW>::r(x / (1.f + expf(-x)));   // SiLU
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -385,7 +398,7 @@ vb_router_kernel(const TE* temb, const TW* w, const TW* bias, int64_t w_layer_st
     for (int i = lane; i < embed_dim; i += 32) acc = fmaf(to_f32(row[i]), s_act[i], acc);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) s_logit[o] = acc + to_f32(bias[layer * bias_layer_stride + o]);
+    if (lane == 0) s_logit[o] = RoundLike<TW>::r(acc + to_f32(bias[layer * bias_layer_stride + o]));
   }
   __syncthreads();
   for (int h = threadIdx.x; h < heads; h += blockDim.x) {
@@ -393,7 +406,7 @@ vb_router_kernel(const TE* temb, const TW* w, const TW* bias, int64_t w_layer_st
     const float mx = fmaxf(l0, fmaxf(l1, l2));
     const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
     const float inv = 1.f / (e0 + e1 + e2);
-    const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+    const float p0 = RoundLike<TW>::r(e0 * inv), p1 = RoundLike<TW>::r(e1 * inv), p2 = RoundLike<TW>::r(e2 * inv);
     float* sc = scores + ((static_cast<int64_t>(layer) * batch + b) * heads + h) * 3;
     sc[0] = p0; sc[1] = p1; sc[2] = p2;
     if (b == 0 && branch != nullptr) {   // the first sample decides for the whole batch (wan.py:398)
@@ -401,7 +414,7 @@ vb_router_kernel(const TE* temb, const TW* w, const TW* bias, int64_t w_layer_st
       float bs = p0;
       if (p1 > bs) { best = 1; bs = p1; }
       if (p2 > bs) { best = 2; bs = p2; }
-      if (bs < tau) best = 0;            // NaN tau compares false: no threshold
+      if (bs < RoundLike<TW>::r(tau)) best = 0;            // NaN tau compares false: no threshold
       branch[layer * heads + h] = best;
     }
   }

@@ -68,6 +68,12 @@ def _attn_kwargs(self_attention_kwargs, routing_score, branch):
     return kw
 
 
+def _text_valid_kw(self_attention_kwargs):
+    """{"text_valid": n} when the transformer forward counted the prompt's un-padded tokens once for the whole step."""
+    tv = (self_attention_kwargs or {}).get("text_valid")
+    return {} if tv is None else {"text_valid": tv}
+
+
 def hunyuan_dual_block_routed_forward(self, hidden_states, encoder_hidden_states, temb, attention_mask, freqs_cis,
                                       token_replace_emb=None, first_frame_num_tokens: int = 0,
                                       use_original_attn: bool = False, self_attention_kwargs=None,
@@ -79,7 +85,8 @@ def hunyuan_dual_block_routed_forward(self, hidden_states, encoder_hidden_states
     norm_encoder = ops.ln_modulate(encoder_hidden_states, None, None, c_scale_msa, c_shift_msa, 1e-6)
     if use_original_attn:
         attn_out, ctx_out = self.attn(hidden_states=norm_hidden, encoder_hidden_states=norm_encoder,
-                                      attention_mask=attention_mask, image_rotary_emb=freqs_cis, use_original_attn=True)
+                                      attention_mask=attention_mask, image_rotary_emb=freqs_cis, use_original_attn=True,
+                                      **_text_valid_kw(self_attention_kwargs))
     else:
         if routing_score is None:
             routing_score = self.router(clean_timesteps_emb)
@@ -110,7 +117,7 @@ def hunyuan_single_block_routed_forward(self, hidden_states, encoder_hidden_stat
     if use_original_attn:
         attn_out, ctx_out = self.attn(hidden_states=norm_hidden, encoder_hidden_states=norm_encoder,
                                       attention_mask=attention_mask, image_rotary_emb=image_rotary_emb,
-                                      use_original_attn=True)
+                                      use_original_attn=True, **_text_valid_kw(self_attention_kwargs))
     else:
         if routing_score is None:
             routing_score = self.router(clean_timesteps_emb)
@@ -154,6 +161,8 @@ def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, tim
 
     kwargs = dict(self_attention_kwargs or {})
     tau = kwargs.get("tau_sparse")
+    if batch_size == 1:        # ONE host read per step instead of one per layer (hunyuan.py:169 syncs in every block)
+        kwargs["text_valid"] = int(effective[0].item()) - latent_len
     blocks = list(self.transformer_blocks) + list(self.single_transformer_blocks)
     eval_mode = isinstance(blocks[0].attn.processor, HunyuanVideoFlashAttnProcessorTripleEval)
     if not eval_mode and torch.is_grad_enabled() and any(q.requires_grad for q in blocks[0].router.parameters()):
@@ -161,6 +170,7 @@ def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, tim
         raise NotImplementedError("vorta_b200: router training is not supported yet (no attention backward); run the "
                                   "Train processors under torch.no_grad()")
     scores, branches = route_step([b.router for b in blocks], clean_emb, tau if eval_mode else None)
+    self._vb_last_branches = branches if eval_mode else None      # fp32 decisions of this step, per layer (bench / tests)
     reg_loss = hidden_layer_distill_loss = last_layer_distill_loss = None
     ref_hidden_states = hidden_states.detach().clone() if return_losses else None
     ref_encoder_hidden_states = encoder_hidden_states.detach().clone() if return_losses else None
@@ -174,7 +184,7 @@ def hunyuan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, tim
             with torch.no_grad():                          # reference branch: the un-routed block (:357-368)
                 ref_hidden_states, ref_encoder_hidden_states, _ = block(
                     ref_hidden_states, ref_encoder_hidden_states, temb, attention_mask, image_rotary_emb,
-                    token_replace_emb, 0, use_original_attn=True)
+                    token_replace_emb, 0, use_original_attn=True, self_attention_kwargs=_text_valid_kw(kwargs))
             reg_loss = accumulate_loss(reg_loss, torch.square(score_i[:, :, 0]).mean().float())
             if reture_hidden_layer_distill_loss:
                 hidden_layer_distill_loss = accumulate_loss(

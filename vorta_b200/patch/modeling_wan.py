@@ -119,6 +119,7 @@ def wan_transformer_3d_routed_forward(self, hidden_states: torch.Tensor, timeste
         scores = branches = None
     else:
         scores, branches = route_step([b.router for b in self.blocks], temb, tau if eval_mode else None)
+    self._vb_last_branches = branches if eval_mode else None      # fp32 decisions of this step, per layer (bench / tests)
     ref_hidden_states = hidden_states.detach().clone() if return_losses else None
     for i, block in enumerate(self.blocks):
         if dense_baseline:

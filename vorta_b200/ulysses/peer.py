@@ -30,8 +30,11 @@ _DISABLED_REASON: Optional[str] = None
 
 class PeerExchange:
     """Symmetric receive buffers of one geometry (heads H, local tokens S_loc, world P), all 128-channel bf16:
-    ``qkv`` (3, S, H/P, 128): this rank's head chunk over the full sequence, written by every peer;
-    ``out`` (S_loc, H, 128): this rank's token shard over all heads, written by every peer's attention epilogue.
+    ``qkv`` (3, S + T, H/P, 128): this rank's head chunk over the full sequence, video rows written by every peer,
+                                  the T replicated text rows (HunyuanVideo; T = 0 for Wan) filled locally;
+    ``out`` (S_loc + T, H, 128): this rank's token shard over all heads, written by every peer's attention epilogue;
+                                  text rows of every head are stored to every rank (the head all-gather of
+                                  vorta/attention/hunyuan.py:186-187).
 
     Ordering per layer (all on the caller's stream):
         scatter_qkv -> barrier A -> attention (reads qkv, stores into peers' out) -> barrier B -> consumer reads out.
@@ -39,41 +42,55 @@ class PeerExchange:
     a qkv buffer that is still being read; it reaches the next barrier A only after its own consumer of ``out`` was
     issued, so nobody stores into ``out`` while it is still needed."""
 
-    def __init__(self, heads: int, s_loc: int, device: torch.device):
+    def __init__(self, heads: int, s_loc: int, device: torch.device, text_len: int = 0):
         import torch.distributed._symmetric_memory as symm
         P, rank = SP_STATE.sp_size, SP_STATE.group_local_rank
         self.P, self.rank, self.heads, self.s_loc, self.hp = P, rank, heads, s_loc, heads // P
         self.S = s_loc * P
+        self.text_len = int(text_len)
         group = SP_STATE.group if SP_STATE.group is not None else dist.group.WORLD
-        self.qkv = symm.empty((3, self.S, self.hp, 128), dtype=torch.bfloat16, device=device)
-        self.out = symm.empty((s_loc, heads, 128), dtype=torch.bfloat16, device=device)
+        self.qkv = symm.empty((3, self.S + self.text_len, self.hp, 128), dtype=torch.bfloat16, device=device)
+        self.out = symm.empty((s_loc + self.text_len, heads, 128), dtype=torch.bfloat16, device=device)
         self.h_qkv = symm.rendezvous(self.qkv, group)
         self.h_out = symm.rendezvous(self.out, group)
         self.qkv_ptrs = (C.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])
         self.out_ptrs = [int(p) for p in self.h_out.buffer_ptrs]
 
-    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head_at: Optional[Sequence[int]] = None
+    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head_at: Optional[Sequence[int]] = None,
+                    text: Optional[Sequence[torch.Tensor]] = None
                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  Returns (1, H/P, S, 128) views of the local
-        receive buffer, valid after barrier A (issued here).  ``head_at``: slot -> head table of a balanced placement
-        (``balance.balance_heads``), None = contiguous head chunks."""
+        """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  Returns (1, H/P, S + T, 128) views of the
+        local receive buffer, valid after barrier A (issued here).  ``head_at``: slot -> head table of a balanced
+        placement (``balance.balance_heads``), None = contiguous head chunks.  ``text``: the replicated (1, H, T, 128)
+        text rows of q, k, v; this rank's heads are copied behind the video rows locally (no traffic)."""
         i64x3 = C.c_int64 * 3
         table = (C.c_int32 * self.heads)(*[int(h) for h in head_at]) if head_at is not None else None
         with torch.cuda.device(q.device):
             L.check(L.lib().vb_ulysses_scatter_qkv(
                 q.data_ptr(), k.data_ptr(), v.data_ptr(), i64x3(q.stride(2), k.stride(2), v.stride(2)),
-                i64x3(q.stride(1), k.stride(1), v.stride(1)), self.qkv_ptrs, self.S, self.s_loc, self.heads, self.P,
-                self.rank, table, torch.cuda.current_stream(q.device).cuda_stream))
+                i64x3(q.stride(1), k.stride(1), v.stride(1)), self.qkv_ptrs, self.S + self.text_len, self.s_loc,
+                self.heads, self.P, self.rank, table, torch.cuda.current_stream(q.device).cuda_stream))
+        if self.text_len:
+            lo = self.rank * self.hp
+            mine = list(head_at[lo:lo + self.hp]) if head_at is not None else list(range(lo, lo + self.hp))
+            sel = torch.tensor(mine, device=q.device)
+            for i, t in enumerate(text):          # (1, H, T, 128) -> rows [S, S + T) of my (S + T, hp, 128) buffer
+                self.qkv[i, self.S:].copy_(t[0].index_select(0, sel).transpose(0, 1))
         self.h_qkv.barrier(channel=0)
         return tuple(self.qkv[i].unsqueeze(0).transpose(1, 2) for i in range(3))
 
+    def zero_padded_text(self, text_valid: int) -> None:
+        """Rows of padded text queries are written by nobody (hunyuan.py:176 pads with zeros): clear them locally."""
+        if self.text_len > text_valid:
+            self.out[self.s_loc + text_valid:].zero_()
+
     def finish_out(self) -> torch.Tensor:
-        """Barrier B, then this rank's (1, H, S_loc, 128) view of the gathered outputs."""
+        """Barrier B, then this rank's (1, H, S_loc + T, 128) view of the gathered outputs."""
         self.h_out.barrier(channel=1)
         return self.out.unsqueeze(0).transpose(1, 2)
 
 
-def get_exchange(heads: int, s_loc: int, device: torch.device) -> Optional[PeerExchange]:
+def get_exchange(heads: int, s_loc: int, device: torch.device, text_len: int = 0) -> Optional[PeerExchange]:
     """The cached exchange for this geometry, or None when peer memory is unavailable / disabled
     (VB_ULYSSES=nccl), in which case the caller takes the NCCL path."""
     global _DISABLED_REASON
@@ -81,11 +98,11 @@ def get_exchange(heads: int, s_loc: int, device: torch.device) -> Optional[PeerE
         return None
     if SP_STATE.sp_size > 8 or heads % SP_STATE.sp_size != 0:
         return None
-    key = (heads, s_loc, str(device), SP_STATE.sp_size)
+    key = (heads, s_loc, str(device), SP_STATE.sp_size, int(text_len))
     ex = _EXCHANGES.get(key)
     if ex is None:
         try:
-            ex = PeerExchange(heads, s_loc, device)
+            ex = PeerExchange(heads, s_loc, device, text_len)
         except Exception as e:                      # no P2P mapping on this box: say so once, use NCCL
             _DISABLED_REASON = f"{type(e).__name__}: {e}"
             if SP_STATE.rank == 0:
