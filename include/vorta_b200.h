@@ -34,6 +34,11 @@ extern "C" {
 #define VB_BRANCH_CORESET 1
 #define VB_BRANCH_SLIDING 2
 #define VB_BRANCH_SKIP (-1)
+/* Ulysses work units finer than a head: a full-attention head may be computed by two ranks, each
+ * taking one half of the QUERY work items (the head's keys and values are needed by both).  A head slot with one of
+ * these ids runs full attention for its half of the query rows only and writes only those output rows. */
+#define VB_BRANCH_FULL_LO 3
+#define VB_BRANCH_FULL_HI 4
 
 #define VB_DTYPE_F32 0
 #define VB_DTYPE_BF16 1
@@ -282,6 +287,15 @@ int vb_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const in
                            int32_t heads, int32_t world, int32_t rank, const int32_t* head_at, vb_stream_t stream);
 int vb_ulysses_unpack_heads(const void* recv, void* y, int32_t s_loc, int32_t heads, int32_t world,
                             const int32_t* head_at, vb_stream_t stream);
+/* The same exchange with an explicit placement: entry e sends head entry_head[e] of this rank's S_loc tokens of q, k, v
+ * to slot entry_slot[e] of peer entry_peer[e], whose receive buffer is laid out (3, rows_total, slots, 128).  Ranks may
+ * hold different numbers of heads, and a head may be sent to two peers (VB_BRANCH_FULL_LO / _HI units).  n_entries <= 128;
+ * host pointers. */
+int vb_ulysses_scatter_qkv_slots(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                                 const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
+                                 int32_t slots, int32_t world, int32_t rank, const int32_t* entry_peer,
+                                 const int32_t* entry_slot, const int32_t* entry_head, int32_t n_entries,
+                                 vb_stream_t stream);
 
 #ifdef __cplusplus
 }

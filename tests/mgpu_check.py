@@ -102,9 +102,11 @@ def main():
     from vorta_b200.attention.wan import _top1_branches
     if rank == 0:
         br = _top1_branches(score, 0.3)
+        placed = balance.place_units(br, [6.0, 1.6, 1.0], world, balance.max_slots(H, world),
+                                     allow_split=balance.split_enabled(world))
         print("exchange:", os.environ.get("VB_ULYSSES", "peer"), "| peer disabled reason:", peer.disabled_reason(),
               "| peer exchanges built:", len(peer._EXCHANGES), "| head balancing:", balance.enabled(),
-              "| branches:", br, "| head_at:", balance.balance_heads(br, [6.0, 1.6, 1.0], world), flush=True)
+              "| branches:", br, "| units per rank (head, part):", placed, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

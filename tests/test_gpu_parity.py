@@ -807,3 +807,64 @@ def test_sliding_direct_raster_loads(monkeypatch):
         got = ops.routed_attention(plan, q, k, v, branch=[2, 0, 2])
         monkeypatch.delenv("VB_ATTN_SLIDING_DIRECT", raising=False)
         assert torch.equal(got, want)
+
+
+def test_query_half_units_equal_the_whole_head():
+    """VB_BRANCH_FULL_LO / _HI (Ulysses units finer than a head): the two query halves of a full-attention head, run as
+    separate head slots (as two ranks would), write disjoint rows whose union is bit-identical to the whole head;
+    mixed with the other branches in one launch; with a HunyuanVideo text tail too."""
+    for lat, tile, lw, tl, tv in (((6, 18, 32), (3, 9, 16), (3, 3, 2), 0, 0), ((6, 12, 8), (3, 6, 4), (2, 3, 2), 40, 23)):
+        plan = ops.Plan(lat, tile, (3, 3, 3), lw, 0.5, text_len=tl, text_valid=tv)
+        S, H = plan.seq_len, 4
+        g = torch.Generator().manual_seed(S + 1)
+        q, k, v = (torch.randn((1, S + tl, H, 128), generator=g).to(torch.bfloat16).to(dev()).transpose(1, 2)
+                   for _ in range(3))
+        want = ops.routed_attention(plan, q, k, v, branch=[0, 1, 2, 0])
+        # slots: head 0 lower half, head 1 (coreset), head 2 (sliding), head 3 whole, head 0 upper half
+        sel = [0, 1, 2, 3, 0]
+        qs, ks, vs = (t[:, sel] for t in (q, k, v))
+        out = torch.full((1, S + tl, H, 128), float("nan"), dtype=torch.bfloat16, device=dev()).transpose(1, 2)
+        ops.routed_attention(plan, qs, ks, vs, branch=[L.BRANCH_FULL_LO, 1, 2, 0, L.BRANCH_FULL_HI], out=out,
+                             out_heads=sel)
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+        # one half alone leaves the other half's rows untouched
+        out2 = torch.zeros_like(out)
+        ops.routed_attention(plan, qs[:, :1], ks[:, :1], vs[:, :1], branch=[L.BRANCH_FULL_LO], out=out2, out_heads=[0])
+        torch.cuda.synchronize()
+        written = out2[0, 0].float().abs().sum(dim=-1) > 0
+        assert 0 < int(written.sum()) < S + tv
+        assert torch.equal(out2[0, 0][written], want[0, 0][written])
+
+
+def test_ulysses_scatter_with_placement_table():
+    """vb_ulysses_scatter_qkv_slots on one GPU, the P ranks' receive buffers emulated as P local buffers: every unit of
+    the placement (uneven head counts, a head sent to two ranks) lands in its slot over the full sequence."""
+    import ctypes as C
+    P, s_loc, H, slots = 4, 24, 8, 4
+    placement = [[(0, 1), (5, 0)], [(0, 2), (1, 0), (2, 0)], [(3, 0), (4, 0), (6, 0), (7, 0)], []]
+    g = torch.Generator().manual_seed(9)
+    shards = [[torch.randn((1, s_loc, H, 128), generator=g).to(torch.bfloat16).to(dev()).transpose(1, 2)
+               for _ in range(3)] for _ in range(P)]
+    S = P * s_loc
+    bufs = [torch.zeros((3, S, slots, 128), dtype=torch.bfloat16, device=dev()) for _ in range(P)]
+    ptrs = (C.c_void_p * P)(*[b.data_ptr() for b in bufs])
+    peers, sl, hd = [], [], []
+    for p, units in enumerate(placement):
+        for slot, (h, _) in enumerate(units):
+            peers.append(p); sl.append(slot); hd.append(h)
+    arr = C.c_int32 * len(peers)
+    i64x3 = C.c_int64 * 3
+    for r in range(P):
+        q, k, v = shards[r]
+        L.check(L.lib().vb_ulysses_scatter_qkv_slots(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), i64x3(q.stride(2), k.stride(2), v.stride(2)),
+            i64x3(q.stride(1), k.stride(1), v.stride(1)), ptrs, S, s_loc, slots, P, r, arr(*peers), arr(*sl), arr(*hd),
+            len(peers), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    full = [torch.cat([shards[r][t] for r in range(P)], dim=2) for t in range(3)]          # (1, H, S, 128)
+    for p, units in enumerate(placement):
+        for slot, (h, _) in enumerate(units):
+            for t in range(3):
+                assert torch.equal(bufs[p][t, :, slot], full[t][0, h])
+        assert bufs[p][:, :, len(units):].abs().max().item() == 0 if len(units) < slots else True

@@ -302,3 +302,38 @@ def test_sliding_work_items_cover_every_query_once_with_its_window(lat, tile, wi
         assert n_split > 0 and n_single <= 2
     else:                               # mixed with natural two-tile items: leftovers stay single
         assert n_split == 0
+
+
+def test_placement_with_query_half_units():
+    """balance.place_units: deterministic; every head is held exactly once — whole, or as a lower and an upper query
+    half (full-attention heads only); at most `slots` units per rank; never worse than the whole-head placement, and
+    clearly better where a rank holds only a few heads (HunyuanVideo: 24 heads on 8 ranks)."""
+    import random
+    from vorta_b200.ulysses import balance
+    costs = [6.5, 1.8, 1.25]
+    rnd = random.Random(3)
+    gain = []
+    for H, P in ((40, 8), (24, 8), (40, 4), (12, 2), (24, 4)):
+        slots = balance.max_slots(H, P)
+        for _ in range(10):
+            branch = [rnd.choice([0, 1, 2]) for _ in range(H)]
+            placed = balance.place_units(branch, costs, P, slots)
+            assert placed == balance.place_units(list(branch), costs, P, slots)
+            assert len(placed) == P and max(len(u) for u in placed) <= slots
+            seen = {}
+            for units in placed:
+                for h, part in units:
+                    seen.setdefault(h, []).append(part)
+            assert sorted(seen) == list(range(H))
+            for h, parts in seen.items():
+                assert sorted(parts) in ([balance.WHOLE], [balance.LOWER, balance.UPPER])
+                assert parts == [balance.WHOLE] or branch[h] == 0
+
+            def load(p):
+                return max(sum(costs[branch[h]] * (1.0 if part == balance.WHOLE else 0.515) for h, part in u) for u in p)
+            whole = balance.place_units(branch, costs, P, slots, allow_split=False)
+            assert all(part == balance.WHOLE for u in whole for _, part in u)
+            assert load(placed) <= load(whole) * (1 + 1e-9)
+            if (H, P) == (24, 8):
+                gain.append(load(whole) / load(placed))
+    assert max(gain) > 1.04 and min(gain) >= 1.0

@@ -20,6 +20,7 @@ VB_ERR_CUDA = -2
 VB_ERR_UNSUPPORTED = -3
 
 BRANCH_FULL, BRANCH_CORESET, BRANCH_SLIDING, BRANCH_SKIP = 0, 1, 2, -1
+BRANCH_FULL_LO, BRANCH_FULL_HI = 3, 4          # full attention over the lower / upper half of the query work items
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ATTN_CORESET_KV_FROM_K = 1
 
@@ -40,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
     "vb_timing_collect_kinds",
     "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_scatter_qkv", "vb_ulysses_unpack_heads",
+    "vb_ulysses_scatter_qkv_slots",
 )
 
 
@@ -147,6 +149,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_ulysses_scatter_qkv.restype = C.c_int
     lib.vb_ulysses_scatter_qkv.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32, i32, i32, i32,
                                            C.POINTER(i32), vp]
+    lib.vb_ulysses_scatter_qkv_slots.restype = C.c_int
+    lib.vb_ulysses_scatter_qkv_slots.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32, i32,
+                                                 i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, vp]
     lib.vb_ulysses_unpack_heads.restype = C.c_int
     lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, C.POINTER(i32), vp]
 

@@ -15,7 +15,7 @@ import torch
 from .. import _lib as L
 from .. import ops
 from ..ulysses import SP_STATE, all_gather, balance, exchange_out, exchange_qkv, local_heads, shrink_dim
-from ..ulysses.peer import get_exchange
+from ..ulysses.peer import get_exchange, layer_placement, local_units
 from ._plans import get_plan, infer_lowres_window
 from .coreset_select import LowresGroupInfo
 from .wan import _top1_branches
@@ -131,22 +131,22 @@ class HunyuanVideoFlashAttnProcessor:
         if SP_STATE.enabled:
             P, r = SP_STATE.sp_size, SP_STATE.group_local_rank
             hp = H // P
-            if branch is not None and balance.enabled():      # cost-balanced head placement (SURVEY.md section 8e)
-                head_at = balance.balance_heads(list(branch), balance.branch_costs(plan), P)
             ex = get_exchange(H, query.shape[2] - text_len, query.device, text_len) if weights is None else None
             if ex is not None:
-                # NVLink peer-memory path (top-1 routing): video rows of Q / K / V are stored straight into the head
-                # owners' buffers, this rank's heads of the replicated text rows are copied locally, and the attention
-                # epilogue stores video rows to the token owner and text rows to every rank
+                # NVLink peer-memory path (top-1 routing): video rows of Q / K / V are stored straight into the buffers
+                # of the ranks that own the head (or a query half of it), the text rows of this rank's heads are copied
+                # locally, and the attention epilogue stores video rows to the token owner and text rows to every rank
+                placement = layer_placement(branch, plan, H, P, ex.slots)
                 parts = [(t[:, :, :-text_len], t[:, :, -text_len:]) for t in (query, key, value)]
-                q, k, v = ex.scatter_qkv(*[p_[0] for p_ in parts], head_at, text=[p_[1] for p_ in parts])
+                q, k, v = ex.scatter_qkv(*[p_[0] for p_ in parts], placement, text=[p_[1] for p_ in parts])
                 ex.zero_padded_text(plan.text_valid)
-                mine = list(head_at[r * hp:(r + 1) * hp]) if head_at is not None else list(range(r * hp, (r + 1) * hp))
-                ops.routed_attention(plan, q, k, v, branch=local_heads(list(branch), H, head_at), flags=flags,
-                                     out_peers=ex.out_ptrs, out_peer_rows=ex.s_loc, out_peer_strides=(0, 128, H * 128),
-                                     out_heads=mine)
+                ids, out_heads = local_units(placement, r, branch, ex.slots)
+                ops.routed_attention(plan, q, k, v, branch=ids, flags=flags, out_peers=ex.out_ptrs,
+                                     out_peer_rows=ex.s_loc, out_peer_strides=(0, 128, H * 128), out_heads=out_heads)
                 out = ex.finish_out()
                 return out[:, :, :-text_len], out[:, :, -text_len:]
+            if branch is not None and balance.enabled():      # cost-balanced head placement (SURVEY.md section 8e)
+                head_at = balance.balance_heads(list(branch), balance.branch_costs(plan), P)
             qv, kv, vv = exchange_qkv(query[:, :, :-text_len], key[:, :, :-text_len], value[:, :, :-text_len],
                                       extra_rows=text_len, head_at=head_at)
             mine = None

@@ -68,6 +68,10 @@ int launch_headnorm_rope(const void* x, const void* weight, const float* cs, con
 int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const int64_t* stride_s,
                                const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int heads,
                                int world, int rank, const int32_t* head_at, cudaStream_t stream);
+int launch_ulysses_scatter_slots(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                                 const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int slots,
+                                 int world, int rank, const int32_t* entry_peer, const int32_t* entry_slot,
+                                 const int32_t* entry_head, int n_entries, cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int make_grid_tensor_map(CUtensorMap* map, const void* base, const int32_t* latent, int32_t tile_w, int64_t heads,
@@ -579,10 +583,12 @@ struct BranchLaunch {
 };
 }  // namespace
 
-// One branch with the head slots it covers.
+// One branch with the head slots it covers; pair_count > 0 restricts it to a sub-range of the schedule's work items
+// (the query halves of VB_BRANCH_FULL_LO / _HI).
 struct Segment {
   BranchLaunch bl;
   std::vector<AttnHead> heads;
+  int pair_begin = 0, pair_count = 0;
 };
 
 // Launch up to kMaxSegments branches as ONE grid (segments in the given order = longest CTAs first), covering
@@ -601,6 +607,7 @@ static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_
     const Segment& sg = *segs[i];
     const BranchLaunch& bl = sg.bl;
     if (sg.heads.empty() || bl.sched->pairs.empty()) continue;
+    if (sg.pair_count < 0 || sg.pair_begin + sg.pair_count > static_cast<int>(bl.sched->pairs.size())) continue;
     VB_REQUIRE(head0 + sg.heads.size() <= static_cast<size_t>(kMaxHeads), VB_ERR_INVALID,
                "more than %d heads in one attention launch", kMaxHeads);
     CUtensorMap* m = tm.m[n_used];
@@ -631,13 +638,26 @@ static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_
       }
     }
     s.n_pairs = static_cast<int32_t>(bl.sched->pairs.size());
+    double seg_flops = bl.sched->flops_per_head;
+    if (sg.pair_count > 0) {      // a query sub-range of the schedule: its share of the head's FLOPs goes by query rows
+      int64_t rows_all = 0, rows_sub = 0;
+      for (size_t i = 0; i < bl.sched->pairs.size(); ++i) {
+        const QPair& qp = bl.sched->pairs[i];
+        const int64_t r = qp.q_rows[0] + (qp.nq == 2 ? qp.q_rows[1] : 0);
+        rows_all += r;
+        if (static_cast<int>(i) >= sg.pair_begin && static_cast<int>(i) < sg.pair_begin + sg.pair_count) rows_sub += r;
+      }
+      s.pairs = bl.sched->d_pairs + sg.pair_begin;
+      s.n_pairs = sg.pair_count;
+      seg_flops *= static_cast<double>(rows_sub) / static_cast<double>(std::max<int64_t>(rows_all, 1));
+    }
     s.n_heads = static_cast<int32_t>(sg.heads.size());
     s.head0 = head0;
     s.cta_begin = static_cast<int32_t>(n_ctas);
     for (size_t h = 0; h < sg.heads.size(); ++h) p.heads[head0 + h] = sg.heads[h];
     head0 += s.n_heads;
     n_ctas += static_cast<int64_t>(s.n_pairs) * s.n_heads * nbatch;
-    flops += bl.sched->flops_per_head * s.n_heads * nbatch;
+    flops += seg_flops * s.n_heads * nbatch;
     ++n_used;
   }
   if (n_used == 0) return VB_OK;
@@ -707,14 +727,14 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   const int N = S + TL;
 
   // heads of each branch, ascending head order (wan.py:409 torch.nonzero)
-  std::vector<int32_t> by_branch[3];
+  std::vector<int32_t> by_branch[5];      // 0 full, 1 coreset, 2 sliding, 3 / 4 full over the lower / upper query half
   for (int h = 0; h < a.heads; ++h) {
     if (blend) {
       for (int e = 0; e < 3; ++e) by_branch[e].push_back(h);
     } else {
       const int e = a.branch[h];
       if (e == VB_BRANCH_SKIP) continue;
-      VB_REQUIRE(e >= 0 && e < 3, VB_ERR_INVALID, "branch id %d of head %d out of range", e, h);
+      VB_REQUIRE(e >= 0 && e < 5, VB_ERR_INVALID, "branch id %d of head %d out of range", e, h);
       by_branch[e].push_back(h);
     }
   }
@@ -750,13 +770,18 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   Segment deferred[kMaxSegments];
   int n_deferred = 0;
   const bool merge = !blend && a.heads <= kMaxHeads && getenv("VB_ATTN_SPLIT_LAUNCHES") == nullptr;
-  auto for_batches = [&](const BranchLaunch& bl, const std::vector<int32_t>& hs, int e, bool slot_is_index) -> int {
+  VB_REQUIRE(!blend || (by_branch[3].empty() && by_branch[4].empty()), VB_ERR_INVALID, "query-half ids need top-1 mode");
+  auto for_batches = [&](const BranchLaunch& bl, const std::vector<int32_t>& hs, int e, bool slot_is_index,
+                         int pair_begin = 0, int pair_count = 0) -> int {
     if (merge) {
       deferred[n_deferred].bl = bl;
       deferred[n_deferred].heads = head_entries(hs, e, slot_is_index, 0);
+      deferred[n_deferred].pair_begin = pair_begin;
+      deferred[n_deferred].pair_count = pair_count;
       ++n_deferred;
       return VB_OK;
     }
+    VB_REQUIRE(pair_count == 0, VB_ERR_UNSUPPORTED, "query-half work units need the merged top-1 launch");
     if (!blend) return run_branch(bl, a, head_entries(hs, e, slot_is_index, 0), 0, a.batch, stream);
     for (int b = 0; b < a.batch; ++b) {
       int r = run_branch(bl, a, head_entries(hs, e, slot_is_index, b), b, 1, stream);
@@ -766,7 +791,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   };
 
   // ---------------- branch 0: full attention, straight from the caller's tensors ----------------
-  if (!by_branch[0].empty()) {
+  if (!by_branch[0].empty() || !by_branch[3].empty() || !by_branch[4].empty()) {
     BranchLaunch bl;
     memset(&bl, 0, sizeof(bl));
     bl.q = static_cast<const __nv_bfloat16*>(a.q);
@@ -775,7 +800,12 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     for (int i = 0; i < 3; ++i) { bl.qs[i] = a.q_stride[i]; bl.ks[i] = a.k_stride[i]; bl.vs[i] = a.v_stride[i]; }
     bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = a.heads;
     bl.sched = &pl->full;
-    if ((rc = for_batches(bl, by_branch[0], 0, false)) != VB_OK) return rc;
+    if (!by_branch[0].empty() && (rc = for_batches(bl, by_branch[0], 0, false)) != VB_OK) return rc;
+    // query halves: work items [0, n / 2) and [n / 2, n) of the same schedule (another rank runs the other half)
+    const int n_items_full = static_cast<int>(pl->full.pairs.size()), n_lo = n_items_full / 2;
+    if (!by_branch[3].empty() && n_lo > 0 && (rc = for_batches(bl, by_branch[3], 0, false, 0, n_lo)) != VB_OK) return rc;
+    if (!by_branch[4].empty() && (rc = for_batches(bl, by_branch[4], 0, false, n_lo, n_items_full - n_lo)) != VB_OK)
+      return rc;
   }
 
   // ---------------- branch 1: coreset ----------------
@@ -1090,6 +1120,18 @@ int vb_ulysses_scatter_qkv(const void* q, const void* k, const void* v, const in
   VB_REQUIRE(q && k && v && stride_s && stride_h && peer_qkv, VB_ERR_INVALID, "null argument");
   int rc = launch_ulysses_scatter_qkv(q, k, v, stride_s, stride_h, peer_qkv, rows_total, s_loc, heads, world, rank,
                                       head_at, static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_ulysses_scatter_qkv_slots(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                                 const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
+                                 int32_t slots, int32_t world, int32_t rank, const int32_t* entry_peer,
+                                 const int32_t* entry_slot, const int32_t* entry_head, int32_t n_entries,
+                                 vb_stream_t stream) {
+  VB_REQUIRE(q && k && v && stride_s && stride_h && peer_qkv && entry_peer && entry_slot && entry_head, VB_ERR_INVALID,
+             "null argument");
+  int rc = launch_ulysses_scatter_slots(q, k, v, stride_s, stride_h, peer_qkv, rows_total, s_loc, slots, world, rank,
+                                        entry_peer, entry_slot, entry_head, n_entries, static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }

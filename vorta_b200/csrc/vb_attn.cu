@@ -124,8 +124,9 @@ struct Item {
 __device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
   Item it;
   it.seg_idx = 0;
-  if (p.n_seg > 1 && item >= p.seg[1].cta_begin) it.seg_idx = 1;
-  if (p.n_seg > 2 && item >= p.seg[2].cta_begin) it.seg_idx = 2;
+#pragma unroll
+  for (int i = 1; i < kMaxSegments; ++i)
+    if (i < p.n_seg && item >= p.seg[i].cta_begin) it.seg_idx = i;
   const AttnSeg& seg = p.seg[it.seg_idx];
   const int local = item - seg.cta_begin;
   const int4* src = reinterpret_cast<const int4*>(seg.pairs + local % seg.n_pairs);

@@ -2,6 +2,8 @@
 // tile-major layout), router head, zero-fill of padded text rows and the Ulysses pack / unpack passes.
 // These are byte / index kernels: 16-byte vector accesses, one warp per small work unit, grids in multiples of
 // the SM count.  No tensor cores here on purpose.
+#include <string.h>
+
 #include "vb_common.cuh"
 
 namespace vb {
@@ -593,6 +595,68 @@ int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, cons
   if (total == 0) return VB_OK;
   const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   vb_ulysses_scatter_qkv_kernel<<<grid, 256, 0, stream>>>(p, tab, rows_total, s_loc, heads, world, rank);
+  VB_CUDA_OK(cudaGetLastError());
+  return VB_OK;
+}
+
+struct SlotTable {
+  uint8_t peer[kMaxHeadTable], slot[kMaxHeadTable], head[kMaxHeadTable];
+};
+// Placement-table form of the scatter: entry e = (peer, slot, head); order (tensor, entry, token) so that consecutive
+// threads walk one peer's rows of one head.
+__global__ void __launch_bounds__(256)
+vb_ulysses_scatter_slots_kernel(const ScatterQkvParams p, const SlotTable tab, int n_entries, int64_t rows_total,
+                                int s_loc, int slots, int rank) {
+  const int64_t per_tensor = static_cast<int64_t>(n_entries) * s_loc;
+  const int64_t total = per_tensor * 3 * 16;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 15);
+    int64_t r = i >> 4;
+    const int t = static_cast<int>(r / per_tensor);
+    r -= t * per_tensor;
+    const int e = static_cast<int>(r % n_entries);      // entry fastest: neighbouring threads read neighbouring heads of a token
+    const int64_t sidx = r / n_entries;
+    const uint4 val = p.src[t][(sidx * p.stride_s[t] + tab.head[e] * p.stride_h[t]) / 8 + c];
+    const int64_t dst = ((static_cast<int64_t>(t) * rows_total + static_cast<int64_t>(rank) * s_loc + sidx) * slots +
+                         tab.slot[e]) * 16 + c;
+    p.peer[tab.peer[e]][dst] = val;
+  }
+}
+
+int launch_ulysses_scatter_slots(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                                 const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int slots,
+                                 int world, int rank, const int32_t* entry_peer, const int32_t* entry_slot,
+                                 const int32_t* entry_head, int n_entries, cudaStream_t stream) {
+  VB_REQUIRE(world > 0 && world <= 8 && slots > 0 && slots <= 255, VB_ERR_INVALID, "world %d / slots %d not supported",
+             world, slots);
+  VB_REQUIRE(n_entries >= 0 && n_entries <= kMaxHeadTable, VB_ERR_UNSUPPORTED, "at most %d placement entries, got %d",
+             kMaxHeadTable, n_entries);
+  ScatterQkvParams p;
+  p.src[0] = static_cast<const uint4*>(q);
+  p.src[1] = static_cast<const uint4*>(k);
+  p.src[2] = static_cast<const uint4*>(v);
+  for (int i = 0; i < 3; ++i) {
+    VB_REQUIRE(stride_s[i] % 8 == 0 && stride_h[i] % 8 == 0, VB_ERR_INVALID, "strides must be multiples of 8 elements");
+    p.stride_s[i] = stride_s[i];
+    p.stride_h[i] = stride_h[i];
+  }
+  for (int i = 0; i < 8; ++i) p.peer[i] = i < world ? static_cast<uint4*>(peer_qkv[i]) : nullptr;
+  SlotTable tab;
+  memset(&tab, 0, sizeof(tab));
+  for (int e = 0; e < n_entries; ++e) {
+    VB_REQUIRE(entry_peer[e] >= 0 && entry_peer[e] < world && entry_slot[e] >= 0 && entry_slot[e] < slots &&
+                   entry_head[e] >= 0 && entry_head[e] < 256,
+               VB_ERR_INVALID, "placement entry %d out of range (peer %d, slot %d, head %d)", e, entry_peer[e],
+               entry_slot[e], entry_head[e]);
+    tab.peer[e] = static_cast<uint8_t>(entry_peer[e]);
+    tab.slot[e] = static_cast<uint8_t>(entry_slot[e]);
+    tab.head[e] = static_cast<uint8_t>(entry_head[e]);
+  }
+  const int64_t total = static_cast<int64_t>(n_entries) * s_loc * 3 * 16;
+  if (total == 0) return VB_OK;
+  const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  vb_ulysses_scatter_slots_kernel<<<grid, 256, 0, stream>>>(p, tab, n_entries, rows_total, s_loc, slots, rank);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }

@@ -50,3 +50,67 @@ def balance_heads(branch: Sequence[int], costs: Sequence[float], world: int) -> 
     if max(load) >= contiguous * (1.0 - 1e-9):
         return None
     return [h for r in range(world) for h in sorted(held[r])]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Placement with work units finer than a head (peer-memory exchange only)
+# ------------------------------------------------------------------------------------------------------------------
+WHOLE, LOWER, UPPER = 0, 1, 2          # part of a head a slot computes: all query rows / lower half / upper half
+_SPLIT_OVERHEAD = 1.03                 # a half head costs a little more than half (second copy of K / V crosses NVLink)
+
+
+def split_enabled(world: int) -> bool:
+    """Query-half units pay off when a rank holds only a few heads (3 at HunyuanVideo P = 8, 5 at Wan-14B P = 8: one full
+    head is 20-40 % of a rank's layer time); VB_ULYSSES_SPLIT=0 / 1 overrides."""
+    env = os.environ.get("VB_ULYSSES_SPLIT")
+    if env is not None:
+        return env != "0"
+    return world >= 4
+
+
+def max_slots(heads: int, world: int) -> int:
+    """Head slots of a rank's receive buffer: room for an uneven placement and for split heads."""
+    hp = heads // world
+    return hp + max(2, (hp + 1) // 2)
+
+
+def place_units(branch: Sequence[int], costs: Sequence[float], world: int, slots: int, allow_split: bool = True
+                ) -> List[List[tuple]]:
+    """Greedy longest-processing-time placement of a layer's heads on ``world`` ranks with at most ``slots`` units per
+    rank.  A unit is (head, part): a whole head, or — for full-attention heads, when that lowers the slowest rank's
+    load — one half of its query work items (the two halves may land on different ranks; both receive the head's K / V).
+    Deterministic in (branch, costs, world, slots): every rank computes the same table.  Returns, per rank, its units
+    in slot order."""
+    H = len(branch)
+    cost = [float(costs[int(e)]) if 0 <= int(e) < len(costs) else 0.0 for e in branch]
+
+    def lpt(units):
+        load = [0.0] * world
+        held: List[List[tuple]] = [[] for _ in range(world)]
+        for c, h, part in sorted(units, key=lambda u: (-u[0], u[1], u[2])):
+            free = [r for r in range(world) if len(held[r]) < slots]
+            if not free:
+                return None, float("inf")
+            r = min(free, key=lambda r: (load[r], r))
+            held[r].append((h, part))
+            load[r] += c
+        return [sorted(x) for x in held], max(load)
+
+    whole = [(cost[h], h, WHOLE) for h in range(H)]
+    best, best_load = lpt(whole)
+    if allow_split:
+        # try splitting the k most expensive full heads, k = 1 .. all (one split alone often does not lower the maximum:
+        # several ranks tie at it); keep the smallest k that gives the lowest maximum load
+        full = sorted((h for h in range(H) if int(branch[h]) == 0), key=lambda h: (-cost[h], h))
+        for k in range(1, len(full) + 1):
+            chosen = set(full[:k])
+            units = [u for u in whole if u[1] not in chosen]
+            for h in full[:k]:
+                half = cost[h] * 0.5 * _SPLIT_OVERHEAD
+                units += [(half, h, LOWER), (half, h, UPPER)]
+            placed, load = lpt(units)
+            if placed is not None and load < best_load * (1.0 - 1e-3):
+                best, best_load = placed, load
+    if best is None:
+        raise ValueError(f"{H} heads do not fit {world} ranks x {slots} slots")
+    return best

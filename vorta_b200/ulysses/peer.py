@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _lib as L
+from . import balance
 from .parallel_states import SP_STATE
 
 _EXCHANGES: Dict[tuple, "PeerExchange"] = {}
@@ -48,34 +49,46 @@ class PeerExchange:
         self.P, self.rank, self.heads, self.s_loc, self.hp = P, rank, heads, s_loc, heads // P
         self.S = s_loc * P
         self.text_len = int(text_len)
+        # head slots of the receive buffer: more than H / P, so that a rank can hold an uneven number of heads and
+        # query halves of full heads (balance.place_units)
+        self.slots = balance.max_slots(heads, P)
         group = SP_STATE.group if SP_STATE.group is not None else dist.group.WORLD
-        self.qkv = symm.empty((3, self.S + self.text_len, self.hp, 128), dtype=torch.bfloat16, device=device)
+        self.qkv = symm.empty((3, self.S + self.text_len, self.slots, 128), dtype=torch.bfloat16, device=device)
         self.out = symm.empty((s_loc + self.text_len, heads, 128), dtype=torch.bfloat16, device=device)
         self.h_qkv = symm.rendezvous(self.qkv, group)
         self.h_out = symm.rendezvous(self.out, group)
         self.qkv_ptrs = (C.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])
         self.out_ptrs = [int(p) for p in self.h_out.buffer_ptrs]
 
-    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, head_at: Optional[Sequence[int]] = None,
-                    text: Optional[Sequence[torch.Tensor]] = None
+    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                    placement: Sequence[Sequence[Tuple[int, int]]], text: Optional[Sequence[torch.Tensor]] = None
                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  Returns (1, H/P, S + T, 128) views of the
-        local receive buffer, valid after barrier A (issued here).  ``head_at``: slot -> head table of a balanced
-        placement (``balance.balance_heads``), None = contiguous head chunks.  ``text``: the replicated (1, H, T, 128)
-        text rows of q, k, v; this rank's heads are copied behind the video rows locally (no traffic)."""
+        """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  ``placement[p]`` = the (head, part) units of
+        rank p in slot order (``balance.place_units`` or ``contiguous_placement``); every head of a unit is stored into
+        that slot of rank p's buffer — a head split into query halves goes to two ranks.  Returns (1, slots, S + T, 128)
+        views of the local receive buffer, valid after barrier A (issued here); only the first len(placement[rank])
+        slots hold data.  ``text``: the replicated (1, H, T, 128) text rows of q, k, v; the rows of this rank's heads are
+        copied behind the video rows locally (no traffic)."""
         i64x3 = C.c_int64 * 3
-        table = (C.c_int32 * self.heads)(*[int(h) for h in head_at]) if head_at is not None else None
+        peers, slots, heads = [], [], []
+        for p, units in enumerate(placement):
+            if len(units) > self.slots:
+                raise ValueError(f"rank {p} was given {len(units)} units for {self.slots} slots")
+            for slot, (h, _part) in enumerate(units):
+                peers.append(p); slots.append(slot); heads.append(int(h))
+        n = len(peers)
+        arr = C.c_int32 * n
         with torch.cuda.device(q.device):
-            L.check(L.lib().vb_ulysses_scatter_qkv(
+            L.check(L.lib().vb_ulysses_scatter_qkv_slots(
                 q.data_ptr(), k.data_ptr(), v.data_ptr(), i64x3(q.stride(2), k.stride(2), v.stride(2)),
                 i64x3(q.stride(1), k.stride(1), v.stride(1)), self.qkv_ptrs, self.S + self.text_len, self.s_loc,
-                self.heads, self.P, self.rank, table, torch.cuda.current_stream(q.device).cuda_stream))
+                self.slots, self.P, self.rank, arr(*peers), arr(*slots), arr(*heads), n,
+                torch.cuda.current_stream(q.device).cuda_stream))
         if self.text_len:
-            lo = self.rank * self.hp
-            mine = list(head_at[lo:lo + self.hp]) if head_at is not None else list(range(lo, lo + self.hp))
+            mine = [h for h, _ in placement[self.rank]]
             sel = torch.tensor(mine, device=q.device)
-            for i, t in enumerate(text):          # (1, H, T, 128) -> rows [S, S + T) of my (S + T, hp, 128) buffer
-                self.qkv[i, self.S:].copy_(t[0].index_select(0, sel).transpose(0, 1))
+            for i, t in enumerate(text):          # (1, H, T, 128) -> rows [S, S + T) of my first len(mine) slots
+                self.qkv[i, self.S:, :len(mine)].copy_(t[0].index_select(0, sel).transpose(0, 1))
         self.h_qkv.barrier(channel=0)
         return tuple(self.qkv[i].unsqueeze(0).transpose(1, 2) for i in range(3))
 
@@ -115,3 +128,35 @@ def get_exchange(heads: int, s_loc: int, device: torch.device, text_len: int = 0
 
 def disabled_reason() -> Optional[str]:
     return _DISABLED_REASON
+
+
+def contiguous_placement(heads: int, world: int):
+    """The reference's chunking (vorta/ulysses/utils.py:60-66) as a placement table: rank r holds whole heads
+    [r * H / P, (r + 1) * H / P)."""
+    hp = heads // world
+    return [[(h, balance.WHOLE) for h in range(r * hp, (r + 1) * hp)] for r in range(world)]
+
+
+def layer_placement(branch: Sequence[int], plan, heads: int, world: int, slots: int):
+    """Placement of one layer's heads for the peer exchange: cost-balanced units (whole heads and, at P >= 4, query
+    halves of full heads) when balancing is on, the contiguous chunks otherwise."""
+    if branch is None or not balance.enabled():
+        return contiguous_placement(heads, world)
+    return balance.place_units(list(branch), balance.branch_costs(plan), world, slots,
+                               allow_split=balance.split_enabled(world))
+
+
+def local_units(placement, rank: int, branch: Sequence[int], slots: int):
+    """(branch id per slot, output head per slot) of this rank for ``vb_attn_fwd``: unused slots are skipped, the halves
+    of a split full head become VB_BRANCH_FULL_LO / _HI."""
+    ids, out_heads = [], []
+    for h, part in placement[rank]:
+        e = int(branch[h])
+        if part != balance.WHOLE:
+            if e != L.BRANCH_FULL:
+                raise ValueError("only full-attention heads are split into query halves")
+            e = L.BRANCH_FULL_LO if part == balance.LOWER else L.BRANCH_FULL_HI
+        ids.append(e)
+        out_heads.append(int(h))
+    pad = slots - len(ids)
+    return ids + [L.BRANCH_SKIP] * pad, out_heads + [0] * pad
