@@ -12,6 +12,7 @@ from its own copy of the routing decisions.
 """
 from __future__ import annotations
 
+import functools
 import os
 from typing import List, Optional, Sequence
 
@@ -80,37 +81,51 @@ def place_units(branch: Sequence[int], costs: Sequence[float], world: int, slots
     rank.  A unit is (head, part): a whole head, or — for full-attention heads, when that lowers the slowest rank's
     load — one half of its query work items (the two halves may land on different ranks; both receive the head's K / V).
     Deterministic in (branch, costs, world, slots): every rank computes the same table.  Returns, per rank, its units
-    in slot order."""
-    H = len(branch)
-    cost = [float(costs[int(e)]) if 0 <= int(e) < len(costs) else 0.0 for e in branch]
+    in slot order.  Results are cached per routing (the same decisions recur across steps and CFG passes)."""
+    return [list(u) for u in _place_cached(tuple(int(e) for e in branch), tuple(float(c) for c in costs), int(world),
+                                           int(slots), bool(allow_split))]
 
-    def lpt(units):
+
+@functools.lru_cache(maxsize=4096)
+def _place_cached(branch: tuple, costs: tuple, world: int, slots: int, allow_split: bool):
+    H = len(branch)
+    cost = [costs[e] if 0 <= e < len(costs) else 0.0 for e in branch]
+
+    def lpt(units):           # units sorted by (-cost, head, part)
         load = [0.0] * world
-        held: List[List[tuple]] = [[] for _ in range(world)]
-        for c, h, part in sorted(units, key=lambda u: (-u[0], u[1], u[2])):
-            free = [r for r in range(world) if len(held[r]) < slots]
-            if not free:
+        count = [0] * world
+        held = [[] for _ in range(world)]
+        for c, h, part in units:
+            best_r, best_l = -1, 0.0
+            for r in range(world):
+                if count[r] < slots and (best_r < 0 or load[r] < best_l):
+                    best_r, best_l = r, load[r]
+            if best_r < 0:
                 return None, float("inf")
-            r = min(free, key=lambda r: (load[r], r))
-            held[r].append((h, part))
-            load[r] += c
-        return [sorted(x) for x in held], max(load)
+            held[best_r].append((h, part))
+            count[best_r] += 1
+            load[best_r] += c
+        return held, max(load)
+
+    def order(units):
+        return sorted(units, key=lambda u: (-u[0], u[1], u[2]))
 
     whole = [(cost[h], h, WHOLE) for h in range(H)]
-    best, best_load = lpt(whole)
+    best, best_load = lpt(order(whole))
     if allow_split:
-        # try splitting the k most expensive full heads, k = 1 .. all (one split alone often does not lower the maximum:
-        # several ranks tie at it); keep the smallest k that gives the lowest maximum load
-        full = sorted((h for h in range(H) if int(branch[h]) == 0), key=lambda h: (-cost[h], h))
-        for k in range(1, len(full) + 1):
+        # try splitting the k most expensive full heads (one split alone often does not lower the maximum: several ranks
+        # tie at it); keep the smallest k that gives the lowest maximum load
+        full = sorted((h for h in range(H) if branch[h] == 0), key=lambda h: (-cost[h], h))
+        tried = sorted({k for k in (1, 2, 3, 4, 6, 8, 12, 16, 24, len(full)) if 1 <= k <= len(full)})
+        for k in tried:
             chosen = set(full[:k])
             units = [u for u in whole if u[1] not in chosen]
             for h in full[:k]:
                 half = cost[h] * 0.5 * _SPLIT_OVERHEAD
                 units += [(half, h, LOWER), (half, h, UPPER)]
-            placed, load = lpt(units)
+            placed, load = lpt(order(units))
             if placed is not None and load < best_load * (1.0 - 1e-3):
                 best, best_load = placed, load
     if best is None:
         raise ValueError(f"{H} heads do not fit {world} ranks x {slots} slots")
-    return best
+    return tuple(tuple(sorted(u)) for u in best)
