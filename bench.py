@@ -373,8 +373,12 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
         fl = t.clone(); dist.all_reduce(fl, op=dist.ReduceOp.SUM)
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         job_flops, attn_ms_max = float(fl[0].item()), float(mx[1].item())
+        each = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(each, t)
+        attn_ms_ranks = [round(float(e[1].item()), 3) for e in each]
     else:
         job_flops, attn_ms_max = attn_flops_step, attn_ms_step
+        attn_ms_ranks = None
     # closed-form cross-check of the library's FLOP counter: head counts x BASELINE.md section 3 formulas (+ the dense
     # cross-attention launches of the Wan blocks: 4 * S * text * 128 per head)
     heads, layers = model_dims(wl)
@@ -388,7 +392,7 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
     torch.cuda.empty_cache()
     return dict(ms=ms, e2e_ms=e2e_ms, clocks=clocks, counts=counts, attn_ms_step=attn_ms_step,
                 attn_flops_step=attn_flops_step, per_kind=per, launches_step=launches_step, job_flops=job_flops,
-                attn_ms_max=attn_ms_max, formula_flops_step=formula,
+                attn_ms_max=attn_ms_max, attn_ms_ranks=attn_ms_ranks, formula_flops_step=formula,
                 h2d=lat_h.numel() * 2 + txt_h.numel() * 2 + 4, d2h=out_h.numel() * 2, cfg=cfg)
 
 
@@ -619,6 +623,8 @@ def run_gpu(args):
     )
     if parity is not None:
         line["parity"] = parity
+    if r["attn_ms_ranks"] is not None:        # attention kernel time per rank: the placement's balance, measured
+        line["attn_kernel_ms_per_rank"] = r["attn_ms_ranks"]
     if world == 1 and rank == 0:
         if not args.no_cpu_baseline:
             lfl, cpu = like_for_like_leg(args, device, with_cpu=True)

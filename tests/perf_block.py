@@ -73,6 +73,11 @@ def main():
         g = 18
         # int64 matching tables over the g-1 margins of every group + int32 kept / dropped token tables (~ S entries)
         line("vb_coreset_select", (row_bytes + heads * S * ((g - 1) / g * 8 + 4)) / 1e6, ms)
+        if name == "hunyuan":      # per-head RMSNorm + RoPE + placement in the joint [video | 256 text] sequence
+            w128 = torch.ones(128, device=dev).bfloat16()
+            joint = torch.empty((1, S + 256, dim), device=dev, dtype=torch.bfloat16)
+            ms = timed([lambda x=x: ops.headnorm_rope(x, w128, 1e-6, heads, cos, sin, out=joint) for x in xs])
+            line("vb_block_headnorm_rope", (2 * row_bytes + S * 64 * 8) / 1e6, ms)
         del xs, qs, plan
         torch.cuda.empty_cache()
 

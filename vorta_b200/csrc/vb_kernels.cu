@@ -34,13 +34,12 @@ __device__ __forceinline__ void bf16x8_to_double(const uint4& v, double (&d)[8])
 //   two similarities are closer than that bound can separate (or a norm leaves the range where the bound holds).
 //   Both paths therefore produce the ranking of the fp64 computation.
 //
-//   fast path : 4 lanes per 256-byte token row (64 B per lane), 8 rows per warp step, every row of the group
-//               requested before the first is used (up to 8 KB in flight per warp).
+//   fast path : 8 lanes per 256-byte token row (32 B per lane), 4 rows per warp step, every row of the group
+//               requested before the first is used (4.6 KB in flight per warp at 17 margins, 24 warps per SM).
 //   bound     : |cos32 - cos| <= 127 u (1 + |cos|) + O(u) < 1.6e-5 with u = 2^-24 when |c|^2, |m|^2 are normal fp32
 //               numbers >= 1e-30; two similarities further apart than kSimGap = 4e-5 cannot swap.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSelectWarps = 8;
-constexpr int kSelectMaxSteps = 4;          // 8 margin rows per step: n_margin <= 32
 constexpr float kSimGap = 4e-5f;
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
@@ -86,14 +85,19 @@ __device__ __noinline__ void select_sims_fp64(const __nv_bfloat16* base, int64_t
   }
 }
 
-// NSTEPS = ceil(n_margin / 8) is a template parameter so that a lane holds exactly the rows it needs (16 registers
-// per step) and three CTAs fit an SM.
+// NSTEPS = ceil(n_margin / 4) is a template parameter so that a lane holds exactly the rows it needs.  8 lanes share a
+// 256-byte token row (32 B per lane), 4 rows per warp step: 2 * NSTEPS 16-byte loads in flight per lane and ~80 registers,
+// so that three CTAs (24 warps, each with a whole group of rows requested) fit an SM.  (Round 1: 4 lanes per row, 128
+// registers, two CTAs per SM: 2.1 TB/s = 0.32 of the copy bandwidth, latency-bound.)
+#ifndef VB_SELECT_CTAS
+#define VB_SELECT_CTAS 3
+#endif
 template <int NSTEPS>
-__global__ void __launch_bounds__(kSelectWarps * 32, 2) vb_coreset_select_kernel(const SelectParams p) {
+__global__ void __launch_bounds__(kSelectWarps * 32, VB_SELECT_CTAS) vb_coreset_select_kernel(const SelectParams p) {
   __shared__ double s_sim[kSelectWarps][32];
   __shared__ float s_simf[kSelectWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lig = lane & 3, rg = lane >> 2;      // lane inside a row's 4-lane group, row slot 0..7 of a step
+  const int lig = lane & 7, rg = lane >> 3;      // lane inside a row's 8-lane group, row slot 0..3 of a step
   const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G;
   const int n_p = p.n_margin - p.n_unpooled;
   const int row_len = p.G * (1 + p.n_unpooled) + p.text_len;   // kept_tok row length
@@ -112,59 +116,59 @@ __global__ void __launch_bounds__(kSelectWarps * 32, 2) vb_coreset_select_kernel
     const int my_tok = lane < p.n_margin ? mtok[lane] : 0;       // lane i holds the token of margin i
 
     // ---- fast path: request every row of the group, then fp32 dot products / norms ----
-    uint4 raw[NSTEPS][4];
+    uint4 raw[NSTEPS][2];
 #pragma unroll
     for (int s = 0; s < NSTEPS; ++s) {
-      const int m = s * 8 + rg;
+      const int m = s * 4 + rg;
       const int tok = __shfl_sync(0xffffffffu, my_tok, m & 31);
       if (m < p.n_margin) {
         const uint4* row = reinterpret_cast<const uint4*>(base + tok * p.stride_s);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) raw[s][j] = ld_stream(row + j * 4 + lig);
+        raw[s][0] = ld_stream(row + lig);            // the 8 lanes of a row cover 128 B per load instruction
+        raw[s][1] = ld_stream(row + 8 + lig);
       }
     }
-    float c[4][8];
+    float c[2][8];
     float cn = 0.f;
     {
       const uint4* crow = reinterpret_cast<const uint4*>(base + ctok * p.stride_s);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bf16x8_to_float(__ldg(crow + j * 4 + lig), c[j]);      // the 8 row groups read the same bytes: L1
+      for (int j = 0; j < 2; ++j) {
+        bf16x8_to_float(__ldg(crow + j * 8 + lig), c[j]);      // the 4 row groups read the same bytes: L1
 #pragma unroll
         for (int i = 0; i < 8; ++i) cn = fmaf(c[j][i], c[j][i], cn);
       }
       cn += __shfl_xor_sync(0xffffffffu, cn, 1);
       cn += __shfl_xor_sync(0xffffffffu, cn, 2);
+      cn += __shfl_xor_sync(0xffffffffu, cn, 4);
     }
     const bool c_ok = cn >= 1e-30f && cn < INFINITY;
     const float c_norm = sqrtf(cn);
 #pragma unroll
     for (int s = 0; s < NSTEPS; ++s) {
-      const int m = s * 8 + rg;
-      {
-        float dot = 0.f, mn = 0.f;
-        if (m < p.n_margin) {
+      const int m = s * 4 + rg;
+      float dot = 0.f, mn = 0.f;
+      if (m < p.n_margin) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float v[8];
-            bf16x8_to_float(raw[s][j], v);
+        for (int j = 0; j < 2; ++j) {
+          float v[8];
+          bf16x8_to_float(raw[s][j], v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              dot = fmaf(c[j][i], v[i], dot);
-              mn = fmaf(v[i], v[i], mn);
-            }
+          for (int i = 0; i < 8; ++i) {
+            dot = fmaf(c[j][i], v[i], dot);
+            mn = fmaf(v[i], v[i], mn);
           }
         }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        mn += __shfl_xor_sync(0xffffffffu, mn, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        mn += __shfl_xor_sync(0xffffffffu, mn, 2);
-        if (lig == 0 && m < p.n_margin) {
-          const bool ok = c_ok && mn >= 1e-30f && mn < INFINITY;
-          const float cosv = ok ? dot / (c_norm * sqrtf(mn)) : NAN;
-          s_simf[warp][m] = cosv;
-          s_sim[warp][m] = static_cast<double>(cosv);
-        }
+      }
+#pragma unroll
+      for (int o = 1; o <= 4; o <<= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        mn += __shfl_xor_sync(0xffffffffu, mn, o);
+      }
+      if (lig == 0 && m < p.n_margin) {
+        const bool ok = c_ok && mn >= 1e-30f && mn < INFINITY;
+        const float cosv = ok ? dot / (c_norm * sqrtf(mn)) : NAN;
+        s_simf[warp][m] = cosv;
+        s_sim[warp][m] = static_cast<double>(cosv);
       }
     }
     __syncwarp();
@@ -216,15 +220,14 @@ int launch_coreset_select(const SelectParams& p, cudaStream_t stream) {
   const int64_t total = static_cast<int64_t>(p.batch) * p.heads * p.G;
   if (total == 0) return VB_OK;
   const int64_t blocks_needed = (total + kSelectWarps - 1) / kSelectWarps;
-  const int grid = static_cast<int>(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
-  VB_REQUIRE(p.n_margin >= 1 && p.n_margin <= 8 * kSelectMaxSteps, VB_ERR_UNSUPPORTED,
+  const int grid = static_cast<int>(blocks_needed < 148 * 12 ? blocks_needed : 148 * 12);
+  VB_REQUIRE(p.n_margin >= 1 && p.n_margin <= 32, VB_ERR_UNSUPPORTED,
              "coreset group of %d margins not supported by the warp-level selection kernel", p.n_margin);
-  switch ((p.n_margin + 7) >> 3) {
-    case 1: vb_coreset_select_kernel<1><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
-    case 2: vb_coreset_select_kernel<2><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
-    case 3: vb_coreset_select_kernel<3><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
-    default: vb_coreset_select_kernel<4><<<grid, kSelectWarps * 32, 0, stream>>>(p); break;
-  }
+  const int steps = (p.n_margin + 3) >> 2;        // 4 margin rows per warp step
+  if (steps <= 2) vb_coreset_select_kernel<2><<<grid, kSelectWarps * 32, 0, stream>>>(p);
+  else if (steps <= 3) vb_coreset_select_kernel<3><<<grid, kSelectWarps * 32, 0, stream>>>(p);
+  else if (steps <= 5) vb_coreset_select_kernel<5><<<grid, kSelectWarps * 32, 0, stream>>>(p);
+  else vb_coreset_select_kernel<8><<<grid, kSelectWarps * 32, 0, stream>>>(p);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }
