@@ -39,6 +39,8 @@ extern "C" {
  * these ids runs full attention for its half of the query rows only and writes only those output rows. */
 #define VB_BRANCH_FULL_LO 3
 #define VB_BRANCH_FULL_HI 4
+/* general form: part k of n equal parts of the head's query work items (n = 2 .. 7); LO / HI are parts 0 / 1 of 2 */
+#define VB_BRANCH_FULL_PART(k, n) (16 + 8 * (n) + (k))
 
 #define VB_DTYPE_F32 0
 #define VB_DTYPE_BF16 1

@@ -828,6 +828,18 @@ def test_query_half_units_equal_the_whole_head():
                              out_heads=sel)
         torch.cuda.synchronize()
         assert torch.equal(out, want)
+        # quarters (VB_BRANCH_FULL_PART(k, 4)) of head 0 in four slots, out of order, next to the whole head 3
+        sel = [0, 0, 3, 0, 0]
+        ids = [16 + 8 * 4 + 0, 16 + 8 * 4 + 2, 0, 16 + 8 * 4 + 3, 16 + 8 * 4 + 1]
+        out4 = torch.full((1, S + tl, H, 128), float("nan"), dtype=torch.bfloat16, device=dev()).transpose(1, 2)
+        ops.routed_attention(plan, q[:, sel], k[:, sel], v[:, sel], branch=ids, out=out4, out_heads=sel)
+        torch.cuda.synchronize()
+        assert torch.equal(out4[:, [0, 3]], want[:, [0, 3]])
+        with pytest.raises(L.VortaB200Error):            # more kinds of parts than a launch has segments for
+            six = [16 + 8 * 4 + i for i in range(4)] + [L.BRANCH_FULL_LO, L.BRANCH_FULL_HI]
+            ops.routed_attention(plan, q[:, [0] * 6], k[:, [0] * 6], v[:, [0] * 6], branch=six)
+        with pytest.raises(ValueError):                  # part 4 of 4 does not exist
+            ops.routed_attention(plan, q[:, :1], k[:, :1], v[:, :1], branch=[16 + 8 * 4 + 4])
         # one half alone leaves the other half's rows untouched
         out2 = torch.zeros_like(out)
         ops.routed_attention(plan, qs[:, :1], ks[:, :1], vs[:, :1], branch=[L.BRANCH_FULL_LO], out=out2, out_heads=[0])

@@ -326,11 +326,15 @@ def test_placement_with_query_half_units():
                     seen.setdefault(h, []).append(part)
             assert sorted(seen) == list(range(H))
             for h, parts in seen.items():
-                assert sorted(parts) in ([balance.WHOLE], [balance.LOWER, balance.UPPER])
-                assert parts == [balance.WHOLE] or branch[h] == 0
+                if parts == [balance.WHOLE]:
+                    continue
+                n = balance.part_kn(parts[0])[1]           # a split head: every part k of n exactly once
+                assert branch[h] == 0 and n in (2, 4)
+                assert sorted(parts) == [balance.part_code(k, n) for k in range(n)]
 
             def load(p):
-                return max(sum(costs[branch[h]] * (1.0 if part == balance.WHOLE else 0.515) for h, part in u) for u in p)
+                return max(sum(costs[branch[h]] * (1.0 if part == balance.WHOLE else 1.03 / balance.part_kn(part)[1])
+                               for h, part in u) for u in p)
             whole = balance.place_units(branch, costs, P, slots, allow_split=False)
             assert all(part == balance.WHOLE for u in whole for _, part in u)
             assert load(placed) <= load(whole) * (1 + 1e-9)

@@ -727,17 +727,32 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   const int N = S + TL;
 
   // heads of each branch, ascending head order (wan.py:409 torch.nonzero)
-  std::vector<int32_t> by_branch[5];      // 0 full, 1 coreset, 2 sliding, 3 / 4 full over the lower / upper query half
+  std::vector<int32_t> by_branch[3];      // 0 full, 1 coreset, 2 sliding
+  // full attention over part k of n of the query work items (VB_BRANCH_FULL_PART; LO / HI = 0 / 1 of 2): heads per (n, k)
+  std::vector<std::pair<int, std::vector<int32_t>>> parts;
   for (int h = 0; h < a.heads; ++h) {
     if (blend) {
       for (int e = 0; e < 3; ++e) by_branch[e].push_back(h);
     } else {
-      const int e = a.branch[h];
+      int e = a.branch[h];
       if (e == VB_BRANCH_SKIP) continue;
-      VB_REQUIRE(e >= 0 && e < 5, VB_ERR_INVALID, "branch id %d of head %d out of range", e, h);
+      if (e == VB_BRANCH_FULL_LO) e = VB_BRANCH_FULL_PART(0, 2);
+      if (e == VB_BRANCH_FULL_HI) e = VB_BRANCH_FULL_PART(1, 2);
+      if (e >= 16) {
+        const int n = (e - 16) >> 3, k = (e - 16) & 7;
+        VB_REQUIRE(n >= 2 && n <= 7 && k < n, VB_ERR_INVALID, "branch id %d of head %d is not a valid query part", e, h);
+        size_t i = 0;
+        while (i < parts.size() && parts[i].first != e) ++i;
+        if (i == parts.size()) parts.push_back({e, {}});
+        parts[i].second.push_back(h);
+        continue;
+      }
+      VB_REQUIRE(e >= 0 && e < 3, VB_ERR_INVALID, "branch id %d of head %d out of range", e, h);
       by_branch[e].push_back(h);
     }
   }
+  VB_REQUIRE(parts.size() + 3 <= static_cast<size_t>(kMaxSegments), VB_ERR_UNSUPPORTED,
+             "at most %d different query parts per launch", kMaxSegments - 3);
   const int64_t need = vb_attn_workspace_bytes(pl, a.batch, a.heads);
   const bool needs_ws = !by_branch[1].empty() || !by_branch[2].empty();
   VB_REQUIRE(!needs_ws || (a.workspace != nullptr && a.workspace_bytes >= need), VB_ERR_INVALID,
@@ -770,7 +785,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   Segment deferred[kMaxSegments];
   int n_deferred = 0;
   const bool merge = !blend && a.heads <= kMaxHeads && getenv("VB_ATTN_SPLIT_LAUNCHES") == nullptr;
-  VB_REQUIRE(!blend || (by_branch[3].empty() && by_branch[4].empty()), VB_ERR_INVALID, "query-half ids need top-1 mode");
+  VB_REQUIRE(!blend || parts.empty(), VB_ERR_INVALID, "query-part ids need top-1 mode");
   auto for_batches = [&](const BranchLaunch& bl, const std::vector<int32_t>& hs, int e, bool slot_is_index,
                          int pair_begin = 0, int pair_count = 0) -> int {
     if (merge) {
@@ -791,7 +806,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   };
 
   // ---------------- branch 0: full attention, straight from the caller's tensors ----------------
-  if (!by_branch[0].empty() || !by_branch[3].empty() || !by_branch[4].empty()) {
+  if (!by_branch[0].empty() || !parts.empty()) {
     BranchLaunch bl;
     memset(&bl, 0, sizeof(bl));
     bl.q = static_cast<const __nv_bfloat16*>(a.q);
@@ -801,11 +816,13 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
     bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = a.heads;
     bl.sched = &pl->full;
     if (!by_branch[0].empty() && (rc = for_batches(bl, by_branch[0], 0, false)) != VB_OK) return rc;
-    // query halves: work items [0, n / 2) and [n / 2, n) of the same schedule (another rank runs the other half)
-    const int n_items_full = static_cast<int>(pl->full.pairs.size()), n_lo = n_items_full / 2;
-    if (!by_branch[3].empty() && n_lo > 0 && (rc = for_batches(bl, by_branch[3], 0, false, 0, n_lo)) != VB_OK) return rc;
-    if (!by_branch[4].empty() && (rc = for_batches(bl, by_branch[4], 0, false, n_lo, n_items_full - n_lo)) != VB_OK)
-      return rc;
+    // query parts: work items [k N / n, (k + 1) N / n) of the same schedule (other ranks run the other parts)
+    const int64_t n_items_full = static_cast<int64_t>(pl->full.pairs.size());
+    for (const auto& part : parts) {
+      const int n = (part.first - 16) >> 3, k = (part.first - 16) & 7;
+      const int begin = static_cast<int>(n_items_full * k / n), end = static_cast<int>(n_items_full * (k + 1) / n);
+      if (end > begin && (rc = for_batches(bl, part.second, 0, false, begin, end - begin)) != VB_OK) return rc;
+    }
   }
 
   // ---------------- branch 1: coreset ----------------

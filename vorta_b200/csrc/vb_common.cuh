@@ -70,7 +70,7 @@ struct AttnHead {
 // One branch of a layer inside an attention launch: its own work table, Q/K/V tensor maps (AttnTmaps::m[i]) and row
 // maps.  A top-1 routed layer runs its (up to) three branches as three segments of ONE launch, longest CTAs first,
 // so the tail of one branch is filled by the next instead of idling the SMs between launches.
-constexpr int kMaxSegments = 5;     // full, full (lower / upper query half), coreset, sliding
+constexpr int kMaxSegments = 8;     // full, up to five kinds of query parts of full heads, coreset, sliding
 struct AttnSeg {
   const QPair* pairs;
   const KvRun* runs;

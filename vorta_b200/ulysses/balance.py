@@ -56,8 +56,21 @@ def balance_heads(branch: Sequence[int], costs: Sequence[float], world: int) -> 
 # ------------------------------------------------------------------------------------------------------------------
 # Placement with work units finer than a head (peer-memory exchange only)
 # ------------------------------------------------------------------------------------------------------------------
-WHOLE, LOWER, UPPER = 0, 1, 2          # part of a head a slot computes: all query rows / lower half / upper half
-_SPLIT_OVERHEAD = 1.03                 # a half head costs a little more than half (second copy of K / V crosses NVLink)
+WHOLE = 0                              # part of a head a slot computes: all of its query work items, or
+
+
+def part_code(k: int, n: int) -> int:
+    """... part k of n equal parts of them (n >= 2), encoded like VB_BRANCH_FULL_PART minus 16."""
+    return 8 * n + k
+
+
+def part_kn(part: int):
+    return part & 7, part >> 3
+
+
+LOWER, UPPER = part_code(0, 2), part_code(1, 2)
+_SPLIT_OVERHEAD = 1.03                 # a part costs a little more than its share (another copy of K / V crosses NVLink)
+_SPLIT_WAYS = (2, 4)                   # halves, quarters
 
 
 def split_enabled(world: int) -> bool:
@@ -72,14 +85,15 @@ def split_enabled(world: int) -> bool:
 def max_slots(heads: int, world: int) -> int:
     """Head slots of a rank's receive buffer: room for an uneven placement and for split heads."""
     hp = heads // world
-    return hp + max(2, (hp + 1) // 2)
+    return min(64, 2 * hp + (1 if hp < 4 else 0))
 
 
 def place_units(branch: Sequence[int], costs: Sequence[float], world: int, slots: int, allow_split: bool = True
                 ) -> List[List[tuple]]:
     """Greedy longest-processing-time placement of a layer's heads on ``world`` ranks with at most ``slots`` units per
     rank.  A unit is (head, part): a whole head, or — for full-attention heads, when that lowers the slowest rank's
-    load — one half of its query work items (the two halves may land on different ranks; both receive the head's K / V).
+    load — one half or quarter of its query work items (``part_code``; the parts may land on different ranks, each
+    receives the head's K / V).
     Deterministic in (branch, costs, world, slots): every rank computes the same table.  Returns, per rank, its units
     in slot order.  Results are cached per routing (the same decisions recur across steps and CFG passes)."""
     return [list(u) for u in _place_cached(tuple(int(e) for e in branch), tuple(float(c) for c in costs), int(world),
@@ -113,19 +127,20 @@ def _place_cached(branch: tuple, costs: tuple, world: int, slots: int, allow_spl
     whole = [(cost[h], h, WHOLE) for h in range(H)]
     best, best_load = lpt(order(whole))
     if allow_split:
-        # try splitting the k most expensive full heads (one split alone often does not lower the maximum: several ranks
-        # tie at it); keep the smallest k that gives the lowest maximum load
+        # try splitting the k most expensive full heads n ways (one split alone often does not lower the maximum:
+        # several ranks tie at it); keep the candidate with the lowest maximum load, the fewest units among equals
         full = sorted((h for h in range(H) if branch[h] == 0), key=lambda h: (-cost[h], h))
         tried = sorted({k for k in (1, 2, 3, 4, 6, 8, 12, 16, 24, len(full)) if 1 <= k <= len(full)})
-        for k in tried:
-            chosen = set(full[:k])
-            units = [u for u in whole if u[1] not in chosen]
-            for h in full[:k]:
-                half = cost[h] * 0.5 * _SPLIT_OVERHEAD
-                units += [(half, h, LOWER), (half, h, UPPER)]
-            placed, load = lpt(order(units))
-            if placed is not None and load < best_load * (1.0 - 1e-3):
-                best, best_load = placed, load
+        for n in _SPLIT_WAYS:
+            for k in tried:
+                chosen = set(full[:k])
+                units = [u for u in whole if u[1] not in chosen]
+                for h in full[:k]:
+                    share = cost[h] / n * _SPLIT_OVERHEAD
+                    units += [(share, h, part_code(i, n)) for i in range(n)]
+                placed, load = lpt(order(units))
+                if placed is not None and load < best_load * (1.0 - 1e-3):
+                    best, best_load = placed, load
     if best is None:
         raise ValueError(f"{H} heads do not fit {world} ranks x {slots} slots")
     return tuple(tuple(sorted(u)) for u in best)

@@ -147,15 +147,15 @@ def layer_placement(branch: Sequence[int], plan, heads: int, world: int, slots: 
 
 
 def local_units(placement, rank: int, branch: Sequence[int], slots: int):
-    """(branch id per slot, output head per slot) of this rank for ``vb_attn_fwd``: unused slots are skipped, the halves
-    of a split full head become VB_BRANCH_FULL_LO / _HI."""
+    """(branch id per slot, output head per slot) of this rank for ``vb_attn_fwd``: unused slots are skipped, the parts
+    of a split full head become VB_BRANCH_FULL_PART(k, n)."""
     ids, out_heads = [], []
     for h, part in placement[rank]:
         e = int(branch[h])
         if part != balance.WHOLE:
             if e != L.BRANCH_FULL:
-                raise ValueError("only full-attention heads are split into query halves")
-            e = L.BRANCH_FULL_LO if part == balance.LOWER else L.BRANCH_FULL_HI
+                raise ValueError("only full-attention heads are split into query parts")
+            e = 16 + part                       # VB_BRANCH_FULL_PART(k, n)
         ids.append(e)
         out_heads.append(int(h))
     pad = slots - len(ids)
