@@ -354,6 +354,9 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
     def reset_counters():          # the timers and launch counters cover EXACTLY the timed steps
         ops.timing_collect()
         ops.stats_reset()
+        if dist_on:
+            from vorta_b200.ulysses import peer
+            peer.nvlink_tx_bytes(reset=True)
 
     sampler.start()
     ms = time_steps(step_resident, args.steps, args.warmup, dist_on, profile=args.profile, after_warmup=reset_counters)
@@ -361,6 +364,10 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
     ops.timing_enable(False)
     kinds = ops.timing_collect_kinds()
     launches_step = ops.stats()[0] / args.steps
+    nvlink_tx_step = None
+    if dist_on:
+        from vorta_b200.ulysses import peer
+        nvlink_tx_step = peer.nvlink_tx_bytes() / args.steps
     per = {}
     for name, (k_ms, k_n, k_fl) in kinds.items():
         per[name] = dict(ms_step=k_ms / args.steps, launches_step=k_n / args.steps, flops_step=k_fl / args.steps)
@@ -392,7 +399,8 @@ def run_workload(wl, args, rank, world, device, with_e2e=True):
     torch.cuda.empty_cache()
     return dict(ms=ms, e2e_ms=e2e_ms, clocks=clocks, counts=counts, attn_ms_step=attn_ms_step,
                 attn_flops_step=attn_flops_step, per_kind=per, launches_step=launches_step, job_flops=job_flops,
-                attn_ms_max=attn_ms_max, attn_ms_ranks=attn_ms_ranks, formula_flops_step=formula,
+                attn_ms_max=attn_ms_max, attn_ms_ranks=attn_ms_ranks, nvlink_tx_step=nvlink_tx_step,
+                formula_flops_step=formula,
                 h2d=lat_h.numel() * 2 + txt_h.numel() * 2 + 4, d2h=out_h.numel() * 2, cfg=cfg)
 
 
@@ -625,6 +633,11 @@ def run_gpu(args):
         line["parity"] = parity
     if r["attn_ms_ranks"] is not None:        # attention kernel time per rank: the placement's balance, measured
         line["attn_kernel_ms_per_rank"] = r["attn_ms_ranks"]
+        line["nvlink"] = dict(
+            tx_bytes_per_step_rank0=r["nvlink_tx_step"], tx_gbs_rank0=r["nvlink_tx_step"] / (r["ms"] * 1e-3) / 1e9,
+            note="bytes rank 0 stores into peers' exchange buffers per step (Q/K/V rows in, output rows out), counted from "
+                 "the placement tables: `nvidia-smi nvlink -gt d` reads N/A on this pool; average rate over the whole step, "
+                 "peak NVLink 5 = 900 GB/s per direction")
     if world == 1 and rank == 0:
         if not args.no_cpu_baseline:
             lfl, cpu = like_for_like_leg(args, device, with_cpu=True)

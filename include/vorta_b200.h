@@ -160,7 +160,8 @@ int vb_gather_rows(const void* src, int64_t src_stride_b, int64_t src_stride_h, 
  *   q, k, v, out: (B, H, S + text_len, 128) bf16 addressed by element strides (batch, head, token)
  *   branch[H]  : VB_BRANCH_* per head (top-1 mode), ignored in blend mode
  *   weights    : NULL for top-1 mode (Eval processor); (B, H, 3) fp32 routing scores for blend mode (Train
- *                processor: every branch on every head, out = sum_e w[b,h,e] * O_e)
+ *                processor: every branch on every head, out = sum_e w[b,h,e] * O_e, summed in fp32 in the workspace
+ *                and rounded to bf16 once; one launch per branch)
  *   flags      : VB_ATTN_* bits
  *   workspace  : device scratch of at least vb_attn_workspace_bytes(...) bytes
  * Text tokens (HunyuanVideo) sit after the video tokens; rows of padded text queries are written as zero.
@@ -198,6 +199,9 @@ typedef struct {
    * the output of local head h.  Lets a rank that holds an arbitrary, cost-balanced subset of the layer's heads
    * (Ulysses) write each head where the token owner expects it. */
   const int32_t* out_heads;
+  /* Blend mode with the routing scores left on the device: (batch, heads, 3) fp32, same meaning as `weights`; when set,
+   * `weights` is ignored and no host copy of the scores is needed (the reference blends device tensors, wan.py:296-300). */
+  const float* weights_device;
 } vb_attn_args;
 
 int64_t vb_attn_workspace_bytes(const vb_plan* plan, int32_t batch, int32_t heads);

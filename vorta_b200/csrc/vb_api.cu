@@ -554,6 +554,7 @@ int64_t vb_attn_workspace_bytes(const vb_plan* pl, int32_t batch, int32_t heads)
   bytes += 3 * align_up(bh * rows_c * kHeadDim * 2, 1024);
   bytes += 2 * align_up(bh * rows_c * 4, 1024);                              // kept_tok for Q and K matchings
   bytes += 2 * align_up(bh * static_cast<int64_t>(pl->G) * std::max(pl->n_p, 1) * 4, 1024);   // dropped_tok
+  bytes += align_up(bh * rows_s * kHeadDim * 4, 1024) + align_up(bh * 3 * 4, 1024);             // blend: fp32 sums, scores
   return bytes + 4096;
 }
 
@@ -582,6 +583,14 @@ struct BranchLaunch {
   const vb_plan* grid_plan;      // non-null: q, k, v are the caller's raster tensors, rows are tile-major (AttnSeg::grid_rows)
 };
 }  // namespace
+
+// Blend-mode state of the launch being assembled (vb_attn_fwd sets it around run_branch)
+struct BlendState {
+  const float* w;
+  float* acc;
+  int stage, branch, heads;
+};
+static thread_local const BlendState* g_blend = nullptr;
 
 // One branch with the head slots it covers; pair_count > 0 restricts it to a sub-range of the schedule's work items
 // (the query halves of VB_BRANCH_FULL_LO / _HI).
@@ -671,6 +680,10 @@ static int launch_segments(const Segment* const* segs, int n_seg, const vb_attn_
   for (int i = 0; i < 8; ++i)
     p.out_peers[i] = i < a.out_peer_count ? static_cast<__nv_bfloat16*>(a.out_peer_ptrs[i]) : nullptr;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+  if (g_blend != nullptr) {
+    p.blend_w = g_blend->w; p.blend_acc = g_blend->acc; p.blend_stage = g_blend->stage;
+    p.blend_heads = g_blend->heads; p.blend_branch = g_blend->branch;
+  }
   p.batch0 = batch0;
   p.dbg = a.debug;
   if (a.debug != nullptr) {   // bring-up only: descriptor stride overrides for the V operand
@@ -719,9 +732,10 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
                   static_cast<int64_t>(a.out_peer_rows) * a.out_peer_count == pl->S),
              VB_ERR_UNSUPPORTED, "peer output needs top-1 routing and out_peer_rows * out_peer_count == video tokens");
   VB_REQUIRE(a.batch > 0 && a.heads > 0, VB_ERR_INVALID, "batch and heads must be positive");
-  VB_REQUIRE(a.weights != nullptr || a.branch != nullptr, VB_ERR_INVALID, "need branch ids or blend weights");
+  VB_REQUIRE(a.weights != nullptr || a.weights_device != nullptr || a.branch != nullptr, VB_ERR_INVALID,
+             "need branch ids or blend weights");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const bool blend = a.weights != nullptr;
+  const bool blend = a.weights != nullptr || a.weights_device != nullptr;
   NvtxRange nvtx_layer(blend ? "vb_attn_fwd (blend)" : "vb_attn_fwd (top-1)");
   const int S = pl->S, TL = pl->d.text_len, TV = pl->d.text_valid;
   const int N = S + TL;
@@ -754,19 +768,39 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
   VB_REQUIRE(parts.size() + 3 <= static_cast<size_t>(kMaxSegments), VB_ERR_UNSUPPORTED,
              "at most %d different query parts per launch", kMaxSegments - 3);
   const int64_t need = vb_attn_workspace_bytes(pl, a.batch, a.heads);
-  const bool needs_ws = !by_branch[1].empty() || !by_branch[2].empty();
+  const bool needs_ws = blend || !by_branch[1].empty() || !by_branch[2].empty();
   VB_REQUIRE(!needs_ws || (a.workspace != nullptr && a.workspace_bytes >= need), VB_ERR_INVALID,
              "workspace too small: %lld < %lld bytes", (long long)a.workspace_bytes, (long long)need);
   Carver ws{static_cast<uint8_t*>(a.workspace), 0, a.workspace_bytes};
   int rc;
+  // blend mode: fp32 partial sums with the output's addressing, and the routing scores on the device
+  BlendState blend_state;
+  memset(&blend_state, 0, sizeof(blend_state));
+  if (blend) {
+    VB_REQUIRE(a.out != nullptr && a.out_peer_count == 0, VB_ERR_UNSUPPORTED, "blend mode writes a local output");
+    int64_t span = 1;       // elements covered by the output strides
+    span += (a.batch - 1) * a.out_stride[0] + (a.heads - 1) * a.out_stride[1] + (static_cast<int64_t>(N) - 1) * a.out_stride[2] +
+            (kHeadDim - 1);
+    blend_state.acc = static_cast<float*>(ws.take(span * 4));
+    float* w_dev = static_cast<float*>(ws.take(static_cast<int64_t>(a.batch) * a.heads * 3 * 4));
+    VB_REQUIRE(blend_state.acc != nullptr && w_dev != nullptr, VB_ERR_INVALID, "workspace exhausted");
+    if (a.weights_device != nullptr) {
+      blend_state.w = a.weights_device;
+    } else {
+      VB_CUDA_OK(cudaMemcpyAsync(w_dev, a.weights, static_cast<size_t>(a.batch) * a.heads * 3 * 4, cudaMemcpyHostToDevice,
+                                 stream));
+      blend_state.w = w_dev;
+    }
+    blend_state.heads = a.heads;
+  }
 
   auto head_entries = [&](const std::vector<int32_t>& hs, int e, bool slot_is_index, int b) {
     std::vector<AttnHead> v(hs.size());
     for (size_t i = 0; i < hs.size(); ++i) {
       v[i].hk = slot_is_index ? static_cast<int32_t>(i) : hs[i];
       v[i].ho = a.out_heads ? a.out_heads[hs[i]] : hs[i];
-      v[i].weight = blend ? a.weights[(static_cast<int64_t>(b) * a.heads + hs[i]) * 3 + e] : 1.f;
-      v[i].flags = (blend && e > 0) ? 1 : 0;
+      v[i].weight = 1.f;
+      v[i].wi = hs[i];
     }
     return v;
   };
@@ -797,12 +831,16 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
       return VB_OK;
     }
     VB_REQUIRE(pair_count == 0, VB_ERR_UNSUPPORTED, "query-half work units need the merged top-1 launch");
-    if (!blend) return run_branch(bl, a, head_entries(hs, e, slot_is_index, 0), 0, a.batch, stream);
-    for (int b = 0; b < a.batch; ++b) {
-      int r = run_branch(bl, a, head_entries(hs, e, slot_is_index, b), b, 1, stream);
-      if (r != VB_OK) return r;
+    // blend: branch e is stage e + 1 of the fp32 accumulation; ONE launch covers every batch element (the scores are read
+    // per (batch, head) from the device table)
+    if (blend) {
+      blend_state.stage = e + 1;
+      blend_state.branch = e;
+      g_blend = &blend_state;
     }
-    return VB_OK;
+    const int r = run_branch(bl, a, head_entries(hs, e, slot_is_index, 0), 0, a.batch, stream);
+    g_blend = nullptr;
+    return r;
   };
 
   // ---------------- branch 0: full attention, straight from the caller's tensors ----------------

@@ -588,8 +588,11 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
       tc_fence_after();
       const bool row_ok = row < pair.q_rows[t];
       const int krow = pair.q_row0[t] + row;      // row in kernel order
-      const float inv = head.weight / l_sum;
-      const bool accumulate = (head.flags & 1) != 0;
+      const int stage = p.blend_stage;
+      const float w_head = stage == 0 ? head.weight
+                                      : __ldg(p.blend_w + (static_cast<int64_t>(batch) * p.blend_heads + head.wi) * 3 +
+                                              p.blend_branch);
+      const float inv = w_head / l_sum;
       int n_dst = 0;
       int64_t dst_tok = 0;
       const int32_t* bc = nullptr;
@@ -632,27 +635,30 @@ vb_attn_fwd_kernel(const __grid_constant__ AttnTmaps tmaps, const __grid_constan
           }
           for (; pe < pe_end; ++pe) {
             __nv_bfloat16* obase = p.out_peer_count > 0 ? p.out_peers[pe] : p.out;
-            uint4* dst = reinterpret_cast<uint4*>(obase + head_off + tok * p.out_stride_s + c * 32);
+            const int64_t off = head_off + tok * p.out_stride_s + c * 32;
+            uint4* dst = reinterpret_cast<uint4*>(obase + off);
+            float4* acc = reinterpret_cast<float4*>(p.blend_acc + off);      // blend mode only
 #pragma unroll
             for (int q4i = 0; q4i < 4; ++q4i) {
               float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[q4i * 8 + i]) * inv;
-              if (accumulate) {
-                const uint4 prev = dst[q4i];
-                const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[2 * i + 0] += __uint_as_float(pw[i] << 16);
-                  f[2 * i + 1] += __uint_as_float(pw[i] & 0xffff0000u);
-                }
+              if (stage >= 2) {                      // add the fp32 partial sum of the earlier branches
+                const float4 a0 = acc[2 * q4i], a1 = acc[2 * q4i + 1];
+                f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+                f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
               }
-              uint4 v;
-              v.x = pack_bf16x2(f[0], f[1]);
-              v.y = pack_bf16x2(f[2], f[3]);
-              v.z = pack_bf16x2(f[4], f[5]);
-              v.w = pack_bf16x2(f[6], f[7]);
-              dst[q4i] = v;
+              if (stage == 1 || stage == 2) {        // not the last branch: keep the sum in fp32
+                acc[2 * q4i] = make_float4(f[0], f[1], f[2], f[3]);
+                acc[2 * q4i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4 v;
+                v.x = pack_bf16x2(f[0], f[1]);
+                v.y = pack_bf16x2(f[2], f[3]);
+                v.z = pack_bf16x2(f[4], f[5]);
+                v.w = pack_bf16x2(f[6], f[7]);
+                dst[q4i] = v;
+              }
             }
           }
         }

@@ -172,13 +172,16 @@ def routed_attention(plan: Plan, q: torch.Tensor, k: torch.Tensor, v: torch.Tens
             # silently cutting the gradient
             raise NotImplementedError("vorta_b200: routed attention has no backward pass yet; run the Train "
                                       "processors under torch.no_grad() or detach the routing scores")
-        w = weights.detach().to(device="cpu", dtype=torch.float32).contiguous()
-        if tuple(w.shape) != (B, H, 3):
-            raise ValueError(f"weights must be (B, H, 3), got {tuple(w.shape)}")
+        if tuple(weights.shape) != (B, H, 3):
+            raise ValueError(f"weights must be (B, H, 3), got {tuple(weights.shape)}")
+        # the routing scores stay on the device (the reference blends device tensors, wan.py:296-300): no host sync
+        w = weights.detach().to(device=q.device, dtype=torch.float32).contiguous()
         keep.append(w)
-        args.weights = C.cast(w.data_ptr(), C.POINTER(C.c_float))
+        args.weights = None
+        args.weights_device = w.data_ptr()
     else:
         args.weights = None
+        args.weights_device = None
     if branch is not None:
         br = (C.c_int32 * H)(*[int(x) for x in branch])
         keep.append(br)

@@ -59,6 +59,9 @@ class PeerExchange:
         self.h_out = symm.rendezvous(self.out, group)
         self.qkv_ptrs = (C.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])
         self.out_ptrs = [int(p) for p in self.h_out.buffer_ptrs]
+        # bytes this rank stores into OTHER ranks' buffers over NVLink, counted from the placement tables (the NVLink data
+        # counters of nvidia-smi read N/A on this pool): "in" = Q/K/V rows of scatter_qkv, "out" = attention output rows
+        self.nvlink_tx_bytes = 0
 
     def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
                     placement: Sequence[Sequence[Tuple[int, int]]], text: Optional[Sequence[torch.Tensor]] = None
@@ -77,6 +80,9 @@ class PeerExchange:
             for slot, (h, _part) in enumerate(units):
                 peers.append(p); slots.append(slot); heads.append(int(h))
         n = len(peers)
+        remote_in = sum(1 for p in peers if p != self.rank)
+        frac_out = sum(1.0 if part == balance.WHOLE else 1.0 / balance.part_kn(part)[1] for _, part in placement[self.rank])
+        self.nvlink_tx_bytes += 3 * self.s_loc * remote_in * 256 + int(frac_out * (self.S - self.s_loc) * 256)
         arr = C.c_int32 * n
         with torch.cuda.device(q.device):
             L.check(L.lib().vb_ulysses_scatter_qkv_slots(
@@ -160,3 +166,12 @@ def local_units(placement, rank: int, branch: Sequence[int], slots: int):
         out_heads.append(int(h))
     pad = slots - len(ids)
     return ids + [L.BRANCH_SKIP] * pad, out_heads + [0] * pad
+
+
+def nvlink_tx_bytes(reset: bool = False) -> int:
+    """Bytes this rank has stored into other ranks' exchange buffers since the last reset (all geometries)."""
+    total = sum(ex.nvlink_tx_bytes for ex in _EXCHANGES.values())
+    if reset:
+        for ex in _EXCHANGES.values():
+            ex.nvlink_tx_bytes = 0
+    return total
