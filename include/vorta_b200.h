@@ -303,6 +303,15 @@ int vb_ulysses_scatter_qkv_slots(const void* q, const void* k, const void* v, co
                                  const int32_t* entry_slot, const int32_t* entry_head, int32_t n_entries,
                                  vb_stream_t stream);
 
+/* One or two of the three tensors only (tensor_mask: bit 0 = q, 1 = k, 2 = v; contiguous bits; unselected pointers may be
+ * NULL) and an optional cap on the grid (max_ctas > 0): lets the host issue K's and V's stores on a side stream while the
+ * next projection GEMM runs, instead of one exposed pass after all three projections. */
+int vb_ulysses_scatter_slots_partial(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                                     const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
+                                     int32_t slots, int32_t world, int32_t rank, const int32_t* entry_peer,
+                                     const int32_t* entry_slot, const int32_t* entry_head, int32_t n_entries,
+                                     int32_t tensor_mask, int32_t max_ctas, vb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

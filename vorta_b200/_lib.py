@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     "vb_stats_reset", "vb_stats_launches", "vb_stats_attn_flops", "vb_timing_enable", "vb_timing_collect",
     "vb_timing_collect_kinds",
     "vb_ulysses_pack_heads", "vb_ulysses_pack_qkv", "vb_ulysses_scatter_qkv", "vb_ulysses_unpack_heads",
-    "vb_ulysses_scatter_qkv_slots",
+    "vb_ulysses_scatter_qkv_slots", "vb_ulysses_scatter_slots_partial",
 )
 
 
@@ -153,6 +153,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.vb_ulysses_scatter_qkv_slots.restype = C.c_int
     lib.vb_ulysses_scatter_qkv_slots.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32, i32,
                                                  i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, vp]
+    lib.vb_ulysses_scatter_slots_partial.restype = C.c_int
+    lib.vb_ulysses_scatter_slots_partial.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), i64, i32,
+                                                     i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32,
+                                                     i32, i32, vp]
     lib.vb_ulysses_unpack_heads.restype = C.c_int
     lib.vb_ulysses_unpack_heads.argtypes = [vp, vp, i32, i32, i32, C.POINTER(i32), vp]
 

@@ -71,7 +71,8 @@ int launch_ulysses_scatter_qkv(const void* q, const void* k, const void* v, cons
 int launch_ulysses_scatter_slots(const void* q, const void* k, const void* v, const int64_t* stride_s,
                                  const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int slots,
                                  int world, int rank, const int32_t* entry_peer, const int32_t* entry_slot,
-                                 const int32_t* entry_head, int n_entries, cudaStream_t stream);
+                                 const int32_t* entry_head, int n_entries, int tensor_mask, int max_ctas,
+                                 cudaStream_t stream);
 int make_qkv_tensor_map(CUtensorMap* map, const void* base, int64_t n_rows, int64_t heads, int64_t batch,
                         int64_t stride_b, int64_t stride_h, int64_t stride_s);
 int make_grid_tensor_map(CUtensorMap* map, const void* base, const int32_t* latent, int32_t tile_w, int64_t heads,
@@ -1186,7 +1187,20 @@ int vb_ulysses_scatter_qkv_slots(const void* q, const void* k, const void* v, co
   VB_REQUIRE(q && k && v && stride_s && stride_h && peer_qkv && entry_peer && entry_slot && entry_head, VB_ERR_INVALID,
              "null argument");
   int rc = launch_ulysses_scatter_slots(q, k, v, stride_s, stride_h, peer_qkv, rows_total, s_loc, slots, world, rank,
-                                        entry_peer, entry_slot, entry_head, n_entries, static_cast<cudaStream_t>(stream));
+                                        entry_peer, entry_slot, entry_head, n_entries, 7, 0,
+                                        static_cast<cudaStream_t>(stream));
+  if (rc == VB_OK) ++g_launches;
+  return rc;
+}
+int vb_ulysses_scatter_slots_partial(const void* q, const void* k, const void* v, const int64_t* stride_s,
+                                     const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int32_t s_loc,
+                                     int32_t slots, int32_t world, int32_t rank, const int32_t* entry_peer,
+                                     const int32_t* entry_slot, const int32_t* entry_head, int32_t n_entries,
+                                     int32_t tensor_mask, int32_t max_ctas, vb_stream_t stream) {
+  VB_REQUIRE(stride_s && stride_h && peer_qkv && entry_peer && entry_slot && entry_head, VB_ERR_INVALID, "null argument");
+  int rc = launch_ulysses_scatter_slots(q, k, v, stride_s, stride_h, peer_qkv, rows_total, s_loc, slots, world, rank,
+                                        entry_peer, entry_slot, entry_head, n_entries, tensor_mask, max_ctas,
+                                        static_cast<cudaStream_t>(stream));
   if (rc == VB_OK) ++g_launches;
   return rc;
 }

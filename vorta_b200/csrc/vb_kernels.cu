@@ -4,6 +4,8 @@
 // the SM count.  No tensor cores here on purpose.
 #include <string.h>
 
+#include <algorithm>
+
 #include "vb_common.cuh"
 
 namespace vb {
@@ -609,15 +611,15 @@ struct SlotTable {
 // threads walk one peer's rows of one head.
 __global__ void __launch_bounds__(256)
 vb_ulysses_scatter_slots_kernel(const ScatterQkvParams p, const SlotTable tab, int n_entries, int64_t rows_total,
-                                int s_loc, int slots, int rank) {
+                                int s_loc, int slots, int rank, int t_begin, int t_count) {
   const int64_t per_tensor = static_cast<int64_t>(n_entries) * s_loc;
-  const int64_t total = per_tensor * 3 * 16;
+  const int64_t total = per_tensor * t_count * 16;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i & 15);
     int64_t r = i >> 4;
-    const int t = static_cast<int>(r / per_tensor);
-    r -= t * per_tensor;
+    const int t = static_cast<int>(r / per_tensor) + t_begin;
+    r -= (t - t_begin) * per_tensor;
     const int e = static_cast<int>(r % n_entries);      // entry fastest: neighbouring threads read neighbouring heads of a token
     const int64_t sidx = r / n_entries;
     const uint4 val = p.src[t][(sidx * p.stride_s[t] + tab.head[e] * p.stride_h[t]) / 8 + c];
@@ -627,10 +629,18 @@ vb_ulysses_scatter_slots_kernel(const ScatterQkvParams p, const SlotTable tab, i
   }
 }
 
+// tensor_mask: bit t set = scatter tensor t (q, k, v = bits 0, 1, 2; the set bits must be contiguous); max_ctas > 0 caps
+// the grid so that the stores can share the GPU with a GEMM running on another stream.
 int launch_ulysses_scatter_slots(const void* q, const void* k, const void* v, const int64_t* stride_s,
                                  const int64_t* stride_h, void* const* peer_qkv, int64_t rows_total, int s_loc, int slots,
                                  int world, int rank, const int32_t* entry_peer, const int32_t* entry_slot,
-                                 const int32_t* entry_head, int n_entries, cudaStream_t stream) {
+                                 const int32_t* entry_head, int n_entries, int tensor_mask, int max_ctas,
+                                 cudaStream_t stream) {
+  VB_REQUIRE(tensor_mask == 1 || tensor_mask == 2 || tensor_mask == 4 || tensor_mask == 3 || tensor_mask == 6 ||
+                 tensor_mask == 7,
+             VB_ERR_INVALID, "tensor_mask %d must select a contiguous range of q, k, v", tensor_mask);
+  const int t_begin = (tensor_mask & 1) ? 0 : ((tensor_mask & 2) ? 1 : 2);
+  const int t_count = __builtin_popcount(static_cast<unsigned>(tensor_mask));
   VB_REQUIRE(world > 0 && world <= 8 && slots > 0 && slots <= 255, VB_ERR_INVALID, "world %d / slots %d not supported",
              world, slots);
   VB_REQUIRE(n_entries >= 0 && n_entries <= kMaxHeadTable, VB_ERR_UNSUPPORTED, "at most %d placement entries, got %d",
@@ -644,6 +654,8 @@ int launch_ulysses_scatter_slots(const void* q, const void* k, const void* v, co
     p.stride_s[i] = stride_s[i];
     p.stride_h[i] = stride_h[i];
   }
+  for (int i = t_begin; i < t_begin + t_count; ++i)
+    VB_REQUIRE(p.src[i] != nullptr, VB_ERR_INVALID, "tensor %d selected by tensor_mask is null", i);
   for (int i = 0; i < 8; ++i) p.peer[i] = i < world ? static_cast<uint4*>(peer_qkv[i]) : nullptr;
   SlotTable tab;
   memset(&tab, 0, sizeof(tab));
@@ -656,10 +668,12 @@ int launch_ulysses_scatter_slots(const void* q, const void* k, const void* v, co
     tab.slot[e] = static_cast<uint8_t>(entry_slot[e]);
     tab.head[e] = static_cast<uint8_t>(entry_head[e]);
   }
-  const int64_t total = static_cast<int64_t>(n_entries) * s_loc * 3 * 16;
+  const int64_t total = static_cast<int64_t>(n_entries) * s_loc * t_count * 16;
   if (total == 0) return VB_OK;
-  const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  vb_ulysses_scatter_slots_kernel<<<grid, 256, 0, stream>>>(p, tab, n_entries, rows_total, s_loc, slots, rank);
+  int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);
+  vb_ulysses_scatter_slots_kernel<<<grid, 256, 0, stream>>>(p, tab, n_entries, rows_total, s_loc, slots, rank, t_begin,
+                                                            t_count);
   VB_CUDA_OK(cudaGetLastError());
   return VB_OK;
 }

@@ -25,6 +25,7 @@ from .. import _lib as L
 from . import balance
 from .parallel_states import SP_STATE
 
+_SIDE_CTAS = int(os.environ.get("VB_ULYSSES_SIDE_CTAS", "32"))      # grid cap of the side-stream store kernels
 _EXCHANGES: Dict[tuple, "PeerExchange"] = {}
 _DISABLED_REASON: Optional[str] = None
 
@@ -62,17 +63,9 @@ class PeerExchange:
         # bytes this rank stores into OTHER ranks' buffers over NVLink, counted from the placement tables (the NVLink data
         # counters of nvidia-smi read N/A on this pool): "in" = Q/K/V rows of scatter_qkv, "out" = attention output rows
         self.nvlink_tx_bytes = 0
+        self._side = None
 
-    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
-                    placement: Sequence[Sequence[Tuple[int, int]]], text: Optional[Sequence[torch.Tensor]] = None
-                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  ``placement[p]`` = the (head, part) units of
-        rank p in slot order (``balance.place_units`` or ``contiguous_placement``); every head of a unit is stored into
-        that slot of rank p's buffer — a head split into query halves goes to two ranks.  Returns (1, slots, S + T, 128)
-        views of the local receive buffer, valid after barrier A (issued here); only the first len(placement[rank])
-        slots hold data.  ``text``: the replicated (1, H, T, 128) text rows of q, k, v; the rows of this rank's heads are
-        copied behind the video rows locally (no traffic)."""
-        i64x3 = C.c_int64 * 3
+    def _tables(self, placement):
         peers, slots, heads = [], [], []
         for p, units in enumerate(placement):
             if len(units) > self.slots:
@@ -84,19 +77,73 @@ class PeerExchange:
         frac_out = sum(1.0 if part == balance.WHOLE else 1.0 / balance.part_kn(part)[1] for _, part in placement[self.rank])
         self.nvlink_tx_bytes += 3 * self.s_loc * remote_in * 256 + int(frac_out * (self.S - self.s_loc) * 256)
         arr = C.c_int32 * n
-        with torch.cuda.device(q.device):
-            L.check(L.lib().vb_ulysses_scatter_qkv_slots(
-                q.data_ptr(), k.data_ptr(), v.data_ptr(), i64x3(q.stride(2), k.stride(2), v.stride(2)),
-                i64x3(q.stride(1), k.stride(1), v.stride(1)), self.qkv_ptrs, self.S + self.text_len, self.s_loc,
-                self.slots, self.P, self.rank, arr(*peers), arr(*slots), arr(*heads), n,
-                torch.cuda.current_stream(q.device).cuda_stream))
+        return arr(*peers), arr(*slots), arr(*heads), n
+
+    def _scatter(self, tensors, tables, mask: int, max_ctas: int = 0) -> None:
+        """tensors: [q, k, v] (1, H, S_loc, 128) views or None for the ones ``mask`` does not select."""
+        i64x3 = C.c_int64 * 3
+        ref = next(t for t in tensors if t is not None)
+        ptr = [t.data_ptr() if t is not None else None for t in tensors]
+        st_s = i64x3(*[t.stride(2) if t is not None else 8 for t in tensors])
+        st_h = i64x3(*[t.stride(1) if t is not None else 8 for t in tensors])
+        peers, slots, heads, n = tables
+        with torch.cuda.device(ref.device):
+            L.check(L.lib().vb_ulysses_scatter_slots_partial(
+                ptr[0], ptr[1], ptr[2], st_s, st_h, self.qkv_ptrs, self.S + self.text_len, self.s_loc, self.slots, self.P,
+                self.rank, peers, slots, heads, n, mask, max_ctas, torch.cuda.current_stream(ref.device).cuda_stream))
+
+    def scatter_qkv(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+                    placement: Sequence[Sequence[Tuple[int, int]]], text: Optional[Sequence[torch.Tensor]] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """q, k, v: (1, H, S_loc, 128) views of this rank's token shard.  ``placement[p]`` = the (head, part) units of
+        rank p in slot order (``balance.place_units`` or ``contiguous_placement``); every head of a unit is stored into
+        that slot of rank p's buffer — a head split into query parts goes to several ranks.  Returns (1, slots, S + T, 128)
+        views of the local receive buffer, valid after barrier A (issued here); only the first len(placement[rank])
+        slots hold data.  ``text``: the replicated (1, H, T, 128) text rows of q, k, v; the rows of this rank's heads are
+        copied behind the video rows locally (no traffic)."""
+        self._scatter([q, k, v], self._tables(placement), 7)
+        return self._finish_scatter(placement, text, q.device)
+
+    def _finish_scatter(self, placement, text, device):
         if self.text_len:
             mine = [h for h, _ in placement[self.rank]]
-            sel = torch.tensor(mine, device=q.device)
+            sel = torch.tensor(mine, device=device)
             for i, t in enumerate(text):          # (1, H, T, 128) -> rows [S, S + T) of my first len(mine) slots
                 self.qkv[i, self.S:, :len(mine)].copy_(t[0].index_select(0, sel).transpose(0, 1))
         self.h_qkv.barrier(channel=0)
         return tuple(self.qkv[i].unsqueeze(0).transpose(1, 2) for i in range(3))
+
+    # ---- overlapped form: K and V leave on a side stream while the next projection GEMM runs -----------------------
+    def overlap_begin(self, placement):
+        """Start an exchange whose tensors are handed over one by one (``overlap_send``) as the projections produce
+        them; ``overlap_end`` issues barrier A.  The side stream has high priority and its store kernels use a capped
+        grid, so they share the GPU with the GEMM of the next projection instead of running exposed after all three."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.qkv.device, priority=-1)
+        self._tables_now = self._tables(placement)
+        self._placement_now = placement
+        self._pending = False
+
+    def overlap_send(self, which: int, x: torch.Tensor, side: bool) -> None:
+        """x: (1, H, S_loc, 128) view of tensor ``which`` (0 = q, 1 = k, 2 = v), complete on the current stream."""
+        tensors = [None, None, None]
+        tensors[which] = x
+        if not side:
+            self._scatter(tensors, self._tables_now, 1 << which)
+            return
+        main = torch.cuda.current_stream(x.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        x.record_stream(self._side)
+        with torch.cuda.stream(self._side):
+            self._scatter(tensors, self._tables_now, 1 << which, max_ctas=_SIDE_CTAS)
+        self._pending = True
+
+    def overlap_end(self, device, text=None):
+        if self._pending:
+            torch.cuda.current_stream(device).wait_stream(self._side)
+        return self._finish_scatter(self._placement_now, text, device)
 
     def zero_padded_text(self, text_valid: int) -> None:
         """Rows of padded text queries are written by nobody (hunyuan.py:176 pads with zeros): clear them locally."""
@@ -175,3 +222,11 @@ def nvlink_tx_bytes(reset: bool = False) -> int:
         for ex in _EXCHANGES.values():
             ex.nvlink_tx_bytes = 0
     return total
+
+
+def overlap_enabled() -> bool:
+    """VB_ULYSSES_OVERLAP=1 (opt-in) sends K and V on a side stream while the next projection GEMM runs.  Measured
+    slower than one pass after all three projections — Wan-14B on 2 GPUs 1688 vs 1620 ms / step, alternating runs on one
+    box (profiles/r2p_*): the cuBLAS GEMMs are persistent over all SMs, so the 32 store CTAs delay whole GEMM waves
+    instead of filling idle SMs, and a 32-CTA grid does not saturate NVLink.  Results are bit-identical either way."""
+    return os.environ.get("VB_ULYSSES_OVERLAP", "0") == "1"
