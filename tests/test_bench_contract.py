@@ -55,4 +55,7 @@ def test_gpu_arm_prints_the_contract_line():
     assert rr["cross_attention"]["launches_per_step"] > 0 and rr["launches_per_step"] > 0
     fl = d["attn_flops_per_step"]
     assert abs(fl["library_counter"] - fl["closed_form"]) <= 1e-6 * fl["closed_form"]
+    # both arms print the SAME config (the reference arm runs "on your arm's config")
+    ref = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    assert ref["config"] == d["config"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])

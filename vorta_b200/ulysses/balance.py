@@ -16,9 +16,10 @@ import functools
 import os
 from typing import List, Optional, Sequence
 
-# measured kernel efficiency relative to the full branch plus the branch's gather passes
-# (profiles/r1_sweep_attn_8k_128k.csv, total_tflops column)
-_BRANCH_OVERHEAD = (1.0, 1.12, 1.25)
+# measured time per algorithmic FLOP relative to the full branch, layout / selection passes included
+# (profiles/r2e_perf_gather.log, r2m_perf_ab_final_kernel.log: full 1330-1370, coreset 1280-1290 incl. select + pool,
+# sliding 1050-1070 kernel / 960-1050 incl. the tile-major pass, TFLOP/s at the Wan-14B geometry)
+_BRANCH_OVERHEAD = (1.0, 1.06, 1.33)
 
 
 def enabled() -> bool:
@@ -26,8 +27,11 @@ def enabled() -> bool:
 
 
 def branch_costs(plan) -> List[float]:
-    """Relative cost of one head of each branch for this geometry (algorithmic FLOPs x measured overhead)."""
-    return [plan.flops_per_head(e) * _BRANCH_OVERHEAD[e] for e in range(3)]
+    """Relative cost of one head of each branch for this geometry (algorithmic FLOPs x measured overhead;
+    VB_ULYSSES_COSTS="1.0,1.12,1.25" overrides the overheads for experiments)."""
+    env = os.environ.get("VB_ULYSSES_COSTS")
+    over = tuple(float(x) for x in env.split(",")) if env else _BRANCH_OVERHEAD
+    return [plan.flops_per_head(e) * over[e] for e in range(3)]
 
 
 def balance_heads(branch: Sequence[int], costs: Sequence[float], world: int) -> Optional[List[int]]:
@@ -70,7 +74,12 @@ def part_kn(part: int):
 
 LOWER, UPPER = part_code(0, 2), part_code(1, 2)
 _SPLIT_OVERHEAD = 1.03                 # a part costs a little more than its share (another copy of K / V crosses NVLink)
-_SPLIT_WAYS = (2, 4)                   # halves, quarters
+
+
+def _split_ways():
+    """n-way splits place_units may use: VB_ULYSSES_SPLIT_WAYS="2" (halves only) or "2,4" (halves and quarters)."""
+    env = os.environ.get("VB_ULYSSES_SPLIT_WAYS", "2,4")
+    return tuple(int(x) for x in env.split(",") if x.strip())
 
 
 def split_enabled(world: int) -> bool:
@@ -97,11 +106,11 @@ def place_units(branch: Sequence[int], costs: Sequence[float], world: int, slots
     Deterministic in (branch, costs, world, slots): every rank computes the same table.  Returns, per rank, its units
     in slot order.  Results are cached per routing (the same decisions recur across steps and CFG passes)."""
     return [list(u) for u in _place_cached(tuple(int(e) for e in branch), tuple(float(c) for c in costs), int(world),
-                                           int(slots), bool(allow_split))]
+                                           int(slots), bool(allow_split), _split_ways())]
 
 
 @functools.lru_cache(maxsize=4096)
-def _place_cached(branch: tuple, costs: tuple, world: int, slots: int, allow_split: bool):
+def _place_cached(branch: tuple, costs: tuple, world: int, slots: int, allow_split: bool, ways: tuple):
     H = len(branch)
     cost = [costs[e] if 0 <= e < len(costs) else 0.0 for e in branch]
 
@@ -131,7 +140,7 @@ def _place_cached(branch: tuple, costs: tuple, world: int, slots: int, allow_spl
         # several ranks tie at it); keep the candidate with the lowest maximum load, the fewest units among equals
         full = sorted((h for h in range(H) if branch[h] == 0), key=lambda h: (-cost[h], h))
         tried = sorted({k for k in (1, 2, 3, 4, 6, 8, 12, 16, 24, len(full)) if 1 <= k <= len(full)})
-        for n in _SPLIT_WAYS:
+        for n in ways:
             for k in tried:
                 chosen = set(full[:k])
                 units = [u for u in whole if u[1] not in chosen]
