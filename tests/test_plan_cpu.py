@@ -304,12 +304,13 @@ def test_sliding_work_items_cover_every_query_once_with_its_window(lat, tile, wi
         assert n_split == 0
 
 
-def test_placement_with_query_half_units():
+def test_placement_with_query_half_units(monkeypatch):
     """balance.place_units: deterministic; every head is held exactly once — whole, or as a lower and an upper query
     half (full-attention heads only); at most `slots` units per rank; never worse than the whole-head placement, and
     clearly better where a rank holds only a few heads (HunyuanVideo: 24 heads on 8 ranks)."""
     import random
     from vorta_b200.ulysses import balance
+    monkeypatch.setenv("VB_ULYSSES_SPLIT_WAYS", "2,4")        # exercise halves and quarters (default: halves)
     costs = [6.5, 1.8, 1.25]
     rnd = random.Random(3)
     gain = []

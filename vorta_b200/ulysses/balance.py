@@ -77,8 +77,9 @@ _SPLIT_OVERHEAD = 1.03                 # a part costs a little more than its sha
 
 
 def _split_ways():
-    """n-way splits place_units may use: VB_ULYSSES_SPLIT_WAYS="2" (halves only) or "2,4" (halves and quarters)."""
-    env = os.environ.get("VB_ULYSSES_SPLIT_WAYS", "2,4")
+    """n-way splits place_units may use: VB_ULYSSES_SPLIT_WAYS="2" (halves only, default) or "2,4" (halves and quarters;
+    measured equal within noise at Wan-14B P = 8, profiles/r2r_scale_n8_placement_ab.log)."""
+    env = os.environ.get("VB_ULYSSES_SPLIT_WAYS", "2")
     return tuple(int(x) for x in env.split(",") if x.strip())
 
 
