@@ -94,11 +94,15 @@ enum {
   VB_EXPORT_MARGIN_INDICES = 1, /* int64 (G, g-1)   == LowresGroupInfo.margin_indices */
   VB_EXPORT_TILE_MAP = 2,       /* int32 (S)  tile-major position -> raster token (tile.py:26-29) */
   VB_EXPORT_TILE_WINDOW = 3,    /* int32 (num_tiles, 6) lo/hi tile coordinate of each query tile's window */
-  VB_EXPORT_SLIDING_RUNS = 4,   /* int32 (runs, 2) start/len in tile-major order */
-  VB_EXPORT_SLIDING_ITEMS = 5   /* int32 (items, 12) work items of the sliding branch in launch order: q_row0[2],
+  VB_EXPORT_SLIDING_RUNS = 4,   /* int32 (runs, 2) start/len of key runs in tile-major order, one consecutive set per
+                                 * window group (query tiles whose clamped windows coincide), then the text queries' */
+  VB_EXPORT_SLIDING_ITEMS = 5,  /* int32 (items, 12) work items of the sliding branch in launch order: q_row0[2],
                                  * q_rows[2], run_begin, run_count, nq, n_blocks, split, run_begin2, run_count2, pad.
-                                 * An item is up to two 128-row query tiles; split = 1 pairs two single-tile leftovers
-                                 * of different tiles, tile 1 then attends to runs [run_begin2, run_begin2 + run_count2) */
+                                 * An item is up to two 128-row query tiles; query rows are positions of
+                                 * VB_EXPORT_SLIDING_QUERY_MAP; split = 1 pairs two single-tile leftovers with different
+                                 * windows, tile 1 then attends to runs [run_begin2, run_begin2 + run_count2) */
+  VB_EXPORT_SLIDING_QUERY_MAP = 6 /* int32 (S + text_len) query position of the sliding branch -> raster token: window
+                                 * group by window group, tiles of a group in tile order, tokens in tile-major order */
 };
 /* Copies a host-side table for parity tests; *bytes is in: capacity, out: size. */
 int vb_plan_export(const vb_plan* plan, int what, void* dst, int64_t* bytes);

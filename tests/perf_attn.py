@@ -32,6 +32,11 @@ def main():
     if os.environ.get("VB_QUICK2"):
         cases = [("wan14 native sliding (5,9,8) H=16", (20, 45, 80), (5, 9, 8), (3, 3, 3), (2, 3, 2), 16, 2),
                  ("wan13 grid sliding (3,10,4) H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 2)]
+    elif os.environ.get("VB_SLIDING"):
+        cases = [("wan14 grid sliding H=16", (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 16, 2),
+                 ("wan14 native sliding (5,9,8) H=16", (20, 45, 80), (5, 9, 8), (3, 3, 3), (2, 3, 2), 16, 2),
+                 ("wan13 grid sliding (3,10,4) H=12", (21, 30, 52), (3, 10, 4), (3, 3, 3), (3, 3, 2), 12, 2),
+                 ("hunyuan 129f grid sliding (3,9,16) H=12", (33, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 12, 2)]
     elif not os.environ.get("VB_QUICK"):
         cases += [("wan14 grid full H=8", (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 8, 0),
                   ("wan14 grid coreset H=16", (21, 45, 80), (3, 9, 16), (3, 3, 3), (3, 3, 2), 16, 1),

@@ -63,16 +63,29 @@ def test_sliding_schedule_equals_reference_mask(golden):
         assert (runs[:, 1] > 0).all()
 
 
+def _window_groups(plan):
+    """Window groups in order of first appearance: (window, [tile ids])."""
+    wins = plan.export(L.EXPORT_TILE_WINDOW).reshape(-1, 6)
+    order, members = [], {}
+    for t, w in enumerate(map(tuple, wins.tolist())):
+        if w not in members:
+            members[w] = []
+            order.append(w)
+        members[w].append(t)
+    return [(w, members[w]) for w in order]
+
+
 def test_run_table_expands_to_mask_rows():
     lat, win, tile = (4, 8, 12), (3, 3, 3), (2, 4, 4)
     plan = ops.Plan(lat, tile, win, (1, 1, 1), n_unpooled=0)
     runs = plan.export(L.EXPORT_SLIDING_RUNS).reshape(-1, 2)
     mask = O.sliding_tile_mask(lat, win, tile)
     tau = plan.tile_tokens
-    # tiles appear in order, each with its own consecutive group of runs whose union is the mask row
+    # window groups appear in order of their first tile, each with its own consecutive set of runs whose union is
+    # the mask row of EVERY tile of the group
     idx = 0
-    for t in range(plan.num_tiles):
-        row = mask[t * tau]
+    for _, tiles in _window_groups(plan):
+        row = mask[tiles[0] * tau]
         want = int(row.sum())
         got = torch.zeros_like(row)
         while want > int(got.sum()):
@@ -80,8 +93,31 @@ def test_run_table_expands_to_mask_rows():
             assert not got[s:s + n].any()
             got[s:s + n] = True
             idx += 1
-        assert torch.equal(got, row)
+        for t in tiles:
+            assert torch.equal(got, mask[t * tau]) and torch.equal(got, mask[(t + 1) * tau - 1])
     assert idx == runs.shape[0]
+
+
+def test_sliding_query_map_is_window_group_order():
+    """VB_EXPORT_SLIDING_QUERY_MAP: a permutation of the raster tokens that lists the tiles window group by window
+    group (tiles whose clamped windows coincide are neighbours), tokens inside a tile in tile.py's order."""
+    for lat, tile, win, tl in [((21, 45, 80), (3, 9, 16), (3, 3, 3), 0), ((21, 30, 52), (3, 10, 4), (3, 3, 3), 0),
+                               ((4, 8, 8), (2, 4, 4), (3, 3, 3), 16), ((6, 6, 8), (1, 3, 4), (3, 1, 3), 0),
+                               ((4, 4, 4), (2, 2, 2), (5, 5, 5), 0)]:
+        plan = ops.Plan(lat, tile, win, (1, 1, 1), n_unpooled=0, text_len=tl, text_valid=tl)
+        S, tau = plan.seq_len, plan.tile_tokens
+        qmap = plan.export(L.EXPORT_SLIDING_QUERY_MAP)
+        tmap = plan.export(L.EXPORT_TILE_MAP)
+        assert qmap.shape[0] == S + tl and np.array_equal(np.sort(qmap), np.arange(S + tl))
+        assert np.array_equal(qmap[S:], np.arange(S, S + tl))
+        want = np.concatenate([tmap[t * tau:(t + 1) * tau] for _, tiles in _window_groups(plan) for t in tiles])
+        assert np.array_equal(qmap[:S], want)
+    # Wan-14B: 45 distinct windows over 175 tiles -> 606 query slots of 128 rows instead of 700
+    plan = ops.Plan((21, 45, 80), (3, 9, 16), (3, 3, 3), (1, 1, 1), n_unpooled=0)
+    groups = _window_groups(plan)
+    assert len(groups) == 45 and sum(len(t) for _, t in groups) == 175
+    items = plan.export(L.EXPORT_SLIDING_ITEMS).reshape(-1, 12)
+    assert int(items[:, 6].sum()) == sum(-(-len(t) * 432 // 128) for _, t in groups) == 606
 
 
 def test_baseline_shapes_build():
@@ -243,17 +279,20 @@ def test_router_checkpoint_roundtrip_with_reference_key_names(tmp_path):
     ((6, 6, 8), (1, 3, 4), (3, 1, 3), 0, 0),          # tiny tiles (12 tokens), odd tile count
 ])
 def test_sliding_work_items_cover_every_query_once_with_its_window(lat, tile, win, tl, tv):
-    """The work items of the persistent attention kernel (vb_attn.cu): every query row of the tile-major sequence is in
-    exactly one 128-row slot; the run list of its slot is the window of its tile (bit-exact against the oracle's dense
-    mask); items that pair two different tiles ("split") walk the same number of key blocks; items are ordered longest
-    first."""
+    """The work items of the persistent attention kernel (vb_attn.cu): every query position of the sliding branch
+    (VB_EXPORT_SLIDING_QUERY_MAP order) is in exactly one 128-row slot; the run list of its slot is the window of the
+    tile that token belongs to (bit-exact against the oracle's dense mask); items that pair two slots with different
+    windows ("split") walk the same number of key blocks; items are ordered longest first."""
     plan = ops.Plan(lat, tile, win, (1, 1, 1), 0.5, text_len=tl, text_valid=tv, n_unpooled=0)
     items = plan.export(L.EXPORT_SLIDING_ITEMS).reshape(-1, 12)
     runs = plan.export(L.EXPORT_SLIDING_RUNS).reshape(-1, 2)
+    qmap = plan.export(L.EXPORT_SLIDING_QUERY_MAP)
     S, tau = plan.seq_len, plan.tile_tokens
     nt = [lat[d] // tile[d] for d in range(3)]
     wins = O.tile_windows(lat, win, tile)
     dense = O.sliding_tile_mask(lat, win, tile, tl, tv) if S <= 4096 else None     # tile-major index space
+    tile_pos = np.empty(S + tl, dtype=np.int64)      # raster token -> tile-major position
+    tile_pos[plan.export(L.EXPORT_TILE_MAP)] = np.arange(S + tl)
 
     def merged(intervals):
         out = []
@@ -264,10 +303,10 @@ def test_sliding_work_items_cover_every_query_once_with_its_window(lat, tile, wi
                 out.append([a, b])
         return out
 
-    def expected_keys(row):
-        if row >= S:                                   # a valid text query sees every non-pad key
+    def expected_keys(pos):                            # pos: tile-major position of the query
+        if pos >= S:                                   # a valid text query sees every non-pad key
             return [[0, S + tv]]
-        lo, hi = wins[row // tau, :3], wins[row // tau, 3:]
+        lo, hi = wins[pos // tau, :3], wins[pos // tau, 3:]
         iv = [(((x * nt[1] + y) * nt[2] + lo[2]) * tau, ((x * nt[1] + y) * nt[2] + hi[2] + 1) * tau)
               for x in range(lo[0], hi[0] + 1) for y in range(lo[1], hi[1] + 1)]
         if tv:
@@ -286,22 +325,23 @@ def test_sliding_work_items_cover_every_query_once_with_its_window(lat, tile, wi
             seen[q0:q0 + qr] += 1
             mine = [(st, st + ln) for st, ln in runs[b:b + c].tolist()]
             assert sum((e - st + 127) // 128 for st, e in mine) == nblk
-            for r in (q0, q0 + qr - 1):                # first and last row of the slot share the slot's run list
-                assert merged(mine) == expected_keys(r), (q0, qr, r)
+            # every sliding tile the slot touches (its rows may span several tiles of one window group)
+            rows = sorted({q0, q0 + qr - 1} | {r for r in range(q0, q0 + qr) if r < S and r % tau == 0})
+            for r in rows:
+                pos = int(tile_pos[qmap[r]])
+                assert merged(mine) == expected_keys(pos), (q0, qr, r)
                 if dense is not None:
                     keys = torch.zeros(S + tl, dtype=torch.bool)
                     for st, e in mine:
                         keys[st:e] = True
-                    assert torch.equal(keys, dense[r])
+                    assert torch.equal(keys, dense[pos])
         cost.append(nblk * nq)
     assert (seen == 1).all()
     assert cost == sorted(cost, reverse=True)
-    n_single = sum(1 for it in items.tolist() if it[6] == 1)
-    n_split = sum(1 for it in items.tolist() if it[8] == 1)
-    if tau <= 128:                      # single-tile branch: leftovers are paired (at most one odd item per block count)
-        assert n_split > 0 and n_single <= 2
-    else:                               # mixed with natural two-tile items: leftovers stay single
-        assert n_split == 0
+    n_slots = sum(it[6] for it in items.tolist())
+    groups = _window_groups(plan)
+    assert n_slots == sum(-(-len(t) * tau // 128) for _, t in groups) + (-(-tv // 128) if tv else 0)
+    assert n_slots <= plan.num_tiles * -(-tau // 128) + (-(-tv // 128) if tv else 0)
 
 
 def test_placement_with_query_half_units(monkeypatch):

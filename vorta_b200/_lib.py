@@ -29,7 +29,7 @@ ATTN_CORESET_KV_FROM_K = 1
  PLAN_NUM_POOLED, PLAN_KEYS_PER_QUERY, PLAN_SLIDING_PAIRS, PLAN_SLIDING_RUNS) = range(10)
 # vb_plan_export keys
 (EXPORT_CENTER_INDICES, EXPORT_MARGIN_INDICES, EXPORT_TILE_MAP, EXPORT_TILE_WINDOW, EXPORT_SLIDING_RUNS,
- EXPORT_SLIDING_ITEMS) = range(6)
+ EXPORT_SLIDING_ITEMS, EXPORT_SLIDING_QUERY_MAP) = range(7)
 
 # every symbol include/vorta_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (

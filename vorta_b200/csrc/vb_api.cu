@@ -114,8 +114,9 @@ struct Schedule {
   // (sliding tiles of <= 128 tokens, e.g. the 120-token tiles of Wan-1.3B), pair two of them that walk the same number
   // of key blocks into ONE split item: tile 1 keeps its own run list (measured 724 -> 768 TFLOP/s, profiles/r2b_*).
   // A split item stages every K/V block for one tile only, i.e. twice the ring traffic per MMA; mixed with ordinary
-  // two-tile items (the 104-row leftover of a 360-token tile) that cost more than the idle pipeline it fills
-  // (1140 -> 986 TFLOP/s), so those leftovers stay single.  Then order the items longest first (stable): the
+  // two-tile items (the odd last slot of a window group) that cost more than the idle pipeline it fills
+  // (1140 -> 986 TFLOP/s), so those leftovers stay single.  With window groups (vb_plan::groups) all-single schedules
+  // only arise when every group is one tile of <= 128 tokens.  Then order the items longest first (stable): the
   // persistent kernel hands them out greedily.
   void finalize() {
     bool all_single = !pairs.empty();
@@ -193,11 +194,23 @@ struct vb_plan {
   std::vector<int64_t> center, margin;        // (G), (G, g-1)
   std::vector<int32_t> tile_map;              // (S + text_len): tile-major position -> raster token
   std::vector<int32_t> tile_window;           // (n_tiles, 6)
-  Schedule full, coreset, sliding;
+  // Query tiles whose (clamped) windows coincide — the two outermost tiles along every axis — see exactly the same keys.
+  // The sliding branch lays its QUERY rows out window group by window group (keys stay tile-major), so a group of s tiles
+  // is cut into ceil(s * tau / 128) query slots instead of s * ceil(tau / 128): Wan-14B's 432-token tiles fill 606
+  // slots instead of 700, and Wan-1.3B's 120-token tiles pair up inside ordinary two-tile items that share one K/V stream.
+  struct WindowGroup {
+    int lo[3], hi[3];
+    int row0, n_tiles;                        // first row in query order, tiles in the group
+  };
+  std::vector<WindowGroup> groups;
+  std::vector<int32_t> query_map;             // (S + text_len): sliding-branch query position -> raster token
+  Schedule full, coreset, sliding;            // sliding: queries in window-group order
+  Schedule sliding_tiles;                     // one range per tile, queries in tile-major order (raster-load path)
   // device tables
   int32_t* d_center_tok = nullptr;
   int32_t* d_margin_tok = nullptr;
   int32_t* d_tile_map = nullptr;
+  int32_t* d_query_map = nullptr;
 };
 
 static void window_range(int q, int n, int w, int& lo, int& hi) {
@@ -222,62 +235,64 @@ static int build_text_dependent(vb_plan* pl) {
   pl->coreset.clear();
   pl->coreset.runs.push_back({0, pl->S_c + tv});
   pl->coreset.add_query_range(0, pl->S_c + tv, 0, 1, pl->S_c + tv);
-  // ---- sliding tile, tile-major order (sliding_attn_flex.py:93-127)
+  // ---- sliding tile (sliding_attn_flex.py:93-127): keys in tile-major order; one query range per window group
+  //      (sliding) and one per tile (sliding_tiles)
   pl->sliding.clear();
-  pl->tile_window.assign(static_cast<size_t>(pl->n_tiles) * 6, 0);
+  pl->sliding_tiles.clear();
   const int tau = pl->tile_tokens;
-  for (int a = 0; a < pl->nt[0]; ++a)
-    for (int b = 0; b < pl->nt[1]; ++b)
-      for (int c = 0; c < pl->nt[2]; ++c) {
-        int lo[3], hi[3];
-        window_range(a, pl->nt[0], d.window[0], lo[0], hi[0]);
-        window_range(b, pl->nt[1], d.window[1], lo[1], hi[1]);
-        window_range(c, pl->nt[2], d.window[2], lo[2], hi[2]);
-        const int tile_id = (a * pl->nt[1] + b) * pl->nt[2] + c;
-        for (int i = 0; i < 3; ++i) {
-          pl->tile_window[tile_id * 6 + i] = lo[i];
-          pl->tile_window[tile_id * 6 + 3 + i] = hi[i];
+  auto add_window = [&](Schedule& sc, const int* lo, const int* hi, int row0, int n_rows) -> int {
+    const int run_begin = static_cast<int>(sc.runs.size());
+    int64_t keys = 0;
+    for (int x = lo[0]; x <= hi[0]; ++x)
+      for (int y = lo[1]; y <= hi[1]; ++y) {
+        KvRun r;
+        r.start = ((x * pl->nt[1] + y) * pl->nt[2] + lo[2]) * tau;
+        r.len = (hi[2] - lo[2] + 1) * tau;
+        keys += r.len;
+        if (static_cast<int>(sc.runs.size()) > run_begin && sc.runs.back().start + sc.runs.back().len == r.start) {
+          sc.runs.back().len += r.len;   // contiguous in tile-major order: merge
+        } else {
+          sc.runs.push_back(r);
         }
-        const int run_begin = static_cast<int>(pl->sliding.runs.size());
-        int64_t keys = 0;
-        for (int x = lo[0]; x <= hi[0]; ++x)
-          for (int y = lo[1]; y <= hi[1]; ++y) {
-            KvRun r;
-            r.start = ((x * pl->nt[1] + y) * pl->nt[2] + lo[2]) * tau;
-            r.len = (hi[2] - lo[2] + 1) * tau;
-            keys += r.len;
-            if (static_cast<int>(pl->sliding.runs.size()) > run_begin &&
-                pl->sliding.runs.back().start + pl->sliding.runs.back().len == r.start) {
-              pl->sliding.runs.back().len += r.len;   // contiguous in tile-major order: merge
-            } else {
-              pl->sliding.runs.push_back(r);
-            }
-          }
-        if (tv > 0) {   // video queries see the valid text keys (:112)
-          pl->sliding.runs.push_back({S, tv});
-          keys += tv;
-        }
-        const int run_count = static_cast<int>(pl->sliding.runs.size()) - run_begin;
-        VB_REQUIRE(run_count <= 32, VB_ERR_UNSUPPORTED, "sliding window needs %d key runs per tile (max 32)",
-                   run_count);
-        pl->sliding.add_query_range(tile_id * tau, tau, run_begin, run_count, keys);
-        if (tile_id == 0) pl->keys_per_query = keys - tv;
       }
+    if (tv > 0) {   // video queries see the valid text keys (:112)
+      sc.runs.push_back({S, tv});
+      keys += tv;
+    }
+    const int run_count = static_cast<int>(sc.runs.size()) - run_begin;
+    VB_REQUIRE(run_count <= 32, VB_ERR_UNSUPPORTED, "sliding window needs %d key runs per tile (max 32)", run_count);
+    sc.add_query_range(row0, n_rows, run_begin, run_count, keys);
+    if (row0 == 0) pl->keys_per_query = keys - tv;
+    return VB_OK;
+  };
+  for (const vb_plan::WindowGroup& g : pl->groups) {
+    const int rc = add_window(pl->sliding, g.lo, g.hi, g.row0, g.n_tiles * tau);
+    if (rc != VB_OK) return rc;
+  }
+  for (int tile_id = 0; tile_id < pl->n_tiles; ++tile_id) {
+    const int32_t* w = &pl->tile_window[static_cast<size_t>(tile_id) * 6];
+    const int rc = add_window(pl->sliding_tiles, w, w + 3, tile_id * tau, tau);
+    if (rc != VB_OK) return rc;
+  }
   if (tv > 0) {   // valid text queries see every non-pad key (:108); two runs, so that no 128-key block straddles the
                   // video / text boundary (video rows come through the raster-grid tensor map, text rows through the linear one)
-    const int run_begin = static_cast<int>(pl->sliding.runs.size());
-    pl->sliding.runs.push_back({0, S});
-    pl->sliding.runs.push_back({S, tv});
-    pl->sliding.add_query_range(S, tv, run_begin, 2, S + tv);
+    for (Schedule* sc : {&pl->sliding, &pl->sliding_tiles}) {
+      const int run_begin = static_cast<int>(sc->runs.size());
+      sc->runs.push_back({0, S});
+      sc->runs.push_back({S, tv});
+      sc->add_query_range(S, tv, run_begin, 2, S + tv);
+    }
   }
   pl->full.finalize();
   pl->coreset.finalize();
   pl->sliding.finalize();
+  pl->sliding_tiles.finalize();
   if (pl->has_device) {
     int rc;
     if ((rc = pl->full.upload()) != VB_OK) return rc;
     if ((rc = pl->coreset.upload()) != VB_OK) return rc;
     if ((rc = pl->sliding.upload()) != VB_OK) return rc;
+    if ((rc = pl->sliding_tiles.upload()) != VB_OK) return rc;
   }
   return VB_OK;
 }
@@ -389,6 +404,47 @@ int vb_plan_create(vb_plan** out, const vb_plan_desc* desc) {
     for (int i = 0; i < d.text_len; ++i) pl->tile_map[pl->S + i] = pl->S + i;
   }
 
+  // ---- windows per tile (sliding_attn_flex.py:118-127), window groups in order of first appearance, and the
+  //      sliding branch's query order: group by group, tiles of a group in tile order, tokens in tile-major order
+  pl->tile_window.assign(static_cast<size_t>(pl->n_tiles) * 6, 0);
+  {
+    std::vector<std::vector<int>> members;
+    const bool group_windows = getenv("VB_ATTN_NO_WINDOW_GROUPS") == nullptr;     // A/B switch: one group per tile
+    for (int a = 0; a < pl->nt[0]; ++a)
+      for (int b = 0; b < pl->nt[1]; ++b)
+        for (int c = 0; c < pl->nt[2]; ++c) {
+          const int tile_id = (a * pl->nt[1] + b) * pl->nt[2] + c;
+          int32_t* w = &pl->tile_window[static_cast<size_t>(tile_id) * 6];
+          int lo, hi;
+          window_range(a, pl->nt[0], d.window[0], lo, hi); w[0] = lo; w[3] = hi;
+          window_range(b, pl->nt[1], d.window[1], lo, hi); w[1] = lo; w[4] = hi;
+          window_range(c, pl->nt[2], d.window[2], lo, hi); w[2] = lo; w[5] = hi;
+          int found = -1;
+          for (size_t g = 0; group_windows && g < pl->groups.size() && found < 0; ++g)
+            if (memcmp(pl->groups[g].lo, w, 3 * sizeof(int)) == 0 && memcmp(pl->groups[g].hi, w + 3, 3 * sizeof(int)) == 0)
+              found = static_cast<int>(g);
+          if (found < 0) {
+            vb_plan::WindowGroup g;
+            for (int i = 0; i < 3; ++i) { g.lo[i] = w[i]; g.hi[i] = w[3 + i]; }
+            g.row0 = 0; g.n_tiles = 0;
+            found = static_cast<int>(pl->groups.size());
+            pl->groups.push_back(g);
+            members.emplace_back();
+          }
+          members[found].push_back(tile_id);
+        }
+    pl->query_map.resize(pl->S + d.text_len);
+    int pos = 0;
+    const int tau = pl->tile_tokens;
+    for (size_t g = 0; g < pl->groups.size(); ++g) {
+      pl->groups[g].row0 = pos;
+      pl->groups[g].n_tiles = static_cast<int>(members[g].size());
+      for (int tile_id : members[g])
+        for (int i = 0; i < tau; ++i) pl->query_map[pos++] = pl->tile_map[static_cast<size_t>(tile_id) * tau + i];
+    }
+    for (int i = 0; i < d.text_len; ++i) pl->query_map[pl->S + i] = pl->S + i;
+  }
+
   // device copies only when a device exists: geometry queries / exports also work on a CPU-only host
   int count = 0;
   if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0) {
@@ -401,7 +457,7 @@ int vb_plan_create(vb_plan** out, const vb_plan_desc* desc) {
     };
     int rc;
     if ((rc = up(&pl->d_center_tok, center32)) != VB_OK || (rc = up(&pl->d_margin_tok, margin32)) != VB_OK ||
-        (rc = up(&pl->d_tile_map, pl->tile_map)) != VB_OK) {
+        (rc = up(&pl->d_tile_map, pl->tile_map)) != VB_OK || (rc = up(&pl->d_query_map, pl->query_map)) != VB_OK) {
       vb_plan_destroy(pl);
       return rc;
     }
@@ -422,6 +478,8 @@ void vb_plan_destroy(vb_plan* pl) {
   pl->full.release();
   pl->coreset.release();
   pl->sliding.release();
+  pl->sliding_tiles.release();
+  if (pl->d_query_map) cudaFree(pl->d_query_map);
   if (pl->d_center_tok) cudaFree(pl->d_center_tok);
   if (pl->d_margin_tok) cudaFree(pl->d_margin_tok);
   if (pl->d_tile_map) cudaFree(pl->d_tile_map);
@@ -467,6 +525,7 @@ int vb_plan_export(const vb_plan* pl, int what, void* dst, int64_t* bytes) {
     case VB_EXPORT_TILE_WINDOW: src = pl->tile_window.data(); n = pl->tile_window.size() * sizeof(int32_t); break;
     case VB_EXPORT_SLIDING_RUNS: src = pl->sliding.runs.data(); n = pl->sliding.runs.size() * sizeof(KvRun); break;
     case VB_EXPORT_SLIDING_ITEMS: src = pl->sliding.pairs.data(); n = pl->sliding.pairs.size() * sizeof(QPair); break;
+    case VB_EXPORT_SLIDING_QUERY_MAP: src = pl->query_map.data(); n = pl->query_map.size() * sizeof(int32_t); break;
     default: VB_REQUIRE(false, VB_ERR_INVALID, "unknown plan export %d", what);
   }
   if (dst != nullptr) {
@@ -966,11 +1025,13 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
       bl.v = static_cast<const __nv_bfloat16*>(a.v);
       for (int i = 0; i < 3; ++i) { bl.qs[i] = a.q_stride[i]; bl.ks[i] = a.k_stride[i]; bl.vs[i] = a.v_stride[i]; }
       bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = a.heads;   // linear maps: text rows keep their place
-      bl.sched = &pl->sliding;
+      bl.sched = &pl->sliding_tiles;
       bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
       bl.grid_plan = pl;
       if ((rc = for_batches(bl, hs, 2, false)) != VB_OK) return rc;
     } else {
+      // layout pass: K and V in tile-major order, Q in window-group order (vb_plan::groups); the epilogue scatters
+      // the output rows back to raster order through the same query map
       NvtxRange nvtx("vb: sliding tile-major layout");
       const int64_t rows = N;
       const int64_t bh = static_cast<int64_t>(a.batch) * nh;
@@ -982,7 +1043,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
       VB_REQUIRE(tq && tk && tv, VB_ERR_INVALID, "workspace exhausted");
       GatherParams gp;
       memset(&gp, 0, sizeof(gp));
-      gp.n_tensors = 3; gp.map = pl->d_tile_map; gp.map_stride_b = 0; gp.map_stride_h = 0;
+      gp.n_tensors = 3; gp.map = pl->d_tile_map; gp.map0 = pl->d_query_map; gp.map_stride_b = 0; gp.map_stride_h = 0;
       gp.src[0] = static_cast<const __nv_bfloat16*>(a.q); gp.dst[0] = tq;
       gp.src[1] = static_cast<const __nv_bfloat16*>(a.k); gp.dst[1] = tk;
       gp.src[2] = static_cast<const __nv_bfloat16*>(a.v); gp.dst[2] = tv;
@@ -1000,7 +1061,7 @@ int vb_attn_fwd(vb_plan* pl, const vb_attn_args* args, vb_stream_t stream_) {
       for (int i = 0; i < 3; ++i) { bl.qs[i] = st[i]; bl.ks[i] = st[i]; bl.vs[i] = st[i]; }
       bl.n_rows_q = S + TV; bl.n_rows_kv = S + TV; bl.n_heads_tensor = nh;
       bl.sched = &pl->sliding;
-      bl.out_map = pl->d_tile_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
+      bl.out_map = pl->d_query_map; bl.out_map_stride_b = 0; bl.out_map_stride_h = 0;
       if ((rc = for_batches(bl, hs, 2, true)) != VB_OK) return rc;
     }
   }

@@ -161,6 +161,7 @@ struct GatherParams {
   int64_t src_stride[3][3];   // [tensor][b, h, s]
   int64_t dst_stride[3];      // b, h, s (shared by the tensors)
   const int32_t* map;
+  const int32_t* map0;        // optional: tensor 0 follows its own row map (same strides)
   int64_t map_stride_b, map_stride_h;
   HeadList head_list;
   int32_t n_tensors, batch, heads, n_rows;

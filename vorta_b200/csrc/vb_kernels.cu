@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(256) vb_gather_rows_kernel(const GatherParams 
         const int hs = static_cast<int>(rr % p.heads);
         const int b = static_cast<int>(rr / p.heads);
         const int h_src = p.head_list.head(hs);
-        const int src_row = p.map ? p.map[b * p.map_stride_b + hs * p.map_stride_h + i] : i;
+        const int32_t* map = (t == 0 && p.map0 != nullptr) ? p.map0 : p.map;
+        const int src_row = map ? map[b * p.map_stride_b + hs * p.map_stride_h + i] : i;
         const __nv_bfloat16* s = p.src[t] + b * p.src_stride[t][0] + h_src * p.src_stride[t][1] +
                                  static_cast<int64_t>(src_row) * p.src_stride[t][2];
         val[u] = ld_stream(reinterpret_cast<const uint4*>(s) + lane16);
