@@ -46,6 +46,12 @@ def main():
         ref_orig = ev(attn, hs, None, None, rot, tau_sparse=0.3, routing_score=score, use_original_attn=True, **kw)
         ctx = FX.det_tensor((1, 40, H * 128), 9).to(dev, torch.bfloat16)
         ref_cross = ev(attn, hs, ctx, None, None, tau_sparse=0.3, routing_score=score, **kw)
+        # batch 2 (the reference's _all_to_all_4D takes any batch, utils.py:15-93): a second sample, its own scores
+        hs2 = torch.cat([hs, FX.det_tensor((1, S, H * 128), 16).to(dev, torch.bfloat16)], dim=0)
+        score2 = torch.cat([score, torch.softmax(FX.det_tensor((1, H, 3), 18, 4.0), -1).to(dev)], dim=0)
+        ref_eval2 = ev(attn, hs2, None, None, rot, tau_sparse=0.3, routing_score=score2, **kw)
+        ref_train2 = tr(attn, hs2, None, None, rot, routing_score=score2, **kw)
+        ref_orig2 = ev(attn, hs2, None, None, rot, tau_sparse=0.3, routing_score=score2, use_original_attn=True, **kw)
     SP_STATE.setup_sp_group(world)
     s_loc = S // world
     mine = hs[:, rank * s_loc:(rank + 1) * s_loc].contiguous()
@@ -59,6 +65,14 @@ def main():
         check("wan original attention", got, ref_orig)
         got = all_gather(ev(attn, mine, ctx, None, None, tau_sparse=0.3, routing_score=score, **kw), dim=1)
         check("wan cross attention", got, ref_cross)
+        mine2 = hs2[:, rank * s_loc:(rank + 1) * s_loc].contiguous()
+        got = all_gather(ev(attn, mine2, None, None, rot, tau_sparse=0.3, routing_score=score2, **kw), dim=1)
+        check("wan eval, batch 2", got, ref_eval2)
+        got = all_gather(tr(attn, mine2, None, None, rot, routing_score=score2, **kw), dim=1)
+        check("wan train (blend), batch 2", got, ref_train2)
+        got = all_gather(ev(attn, mine2, None, None, rot, tau_sparse=0.3, routing_score=score2, use_original_attn=True,
+                            **kw), dim=1)
+        check("wan original attention, batch 2", got, ref_orig2)
     SP_STATE._enabled, SP_STATE._sp_size = False, 1        # single-GPU reference for the next case
 
     # ---------------- Wan dense baseline (apply_sp_flashattn_transformer) under SP: whole DiT step ----------------

@@ -61,16 +61,19 @@ def unpack_heads(recv: torch.Tensor, head_at: Optional[Sequence[int]] = None) ->
 
 def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: int = 0,
                  head_at: Optional[Sequence[int]] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """q, k, v: (1, H, S_loc, 128) views: this rank's token shard, all heads.
-    Each tensor may have its own (token, head) strides.
-    Returns (1, H/P, S + extra_rows, 128) views of token-major memory: this rank's head chunk over the full
+    """q, k, v: (B, H, S_loc, 128) views: this rank's token shard, all heads.
+    Each tensor may have its own (batch, token, head) strides.
+    Returns (B, H/P, S + extra_rows, 128) views of token-major memory: this rank's head chunk over the full
     sequence; ``extra_rows`` uninitialised rows are left at the end for the caller (HunyuanVideo text tokens).
     ``head_at``: slot -> head table of a balanced placement (``balance.balance_heads``); rank r then holds heads
-    ``head_at[r*H/P:(r+1)*H/P]`` instead of the contiguous chunk."""
+    ``head_at[r*H/P:(r+1)*H/P]`` instead of the contiguous chunk.
+    Any batch size, like the reference's ``_all_to_all_4D`` (utils.py:15-93): samples travel one after the other."""
     P = SP_STATE.sp_size
     B, H, s_loc, D = q.shape
     if B != 1:
-        raise ValueError("sequence-parallel attention supports batch size 1 per call (hunyuan.py:168)")
+        parts = [exchange_qkv(q[b:b + 1], k[b:b + 1], v[b:b + 1], extra_rows, head_at) for b in range(B)]
+        # (B, S + extra, hp, D) memory, handed back as the same (B, hp, S + extra, D) view a single sample gets
+        return tuple(torch.cat([p[i].transpose(1, 2) for p in parts], dim=0).transpose(1, 2) for i in range(3))
     if H % P != 0:
         raise ValueError(f"heads {H} must be divisible by the sequence-parallel size {P}")
     for t in (q, k, v):
@@ -95,10 +98,13 @@ def exchange_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, extra_rows: 
 
 
 def exchange_out(o: torch.Tensor, head_at: Optional[Sequence[int]] = None) -> torch.Tensor:
-    """o: (1, H/P, S, 128) view of (1, S, H/P, 128) memory -> (1, H, S_loc, 128) view of (1, S_loc, H, 128).
+    """o: (B, H/P, S, 128) view of (B, S, H/P, 128) memory -> (B, H, S_loc, 128) view of (B, S_loc, H, 128).
     ``head_at`` must be the table the matching ``exchange_qkv`` used; heads come back in their original order."""
     P = SP_STATE.sp_size
     B, hp, S, D = o.shape
+    if B != 1:
+        parts = [exchange_out(o[b:b + 1], head_at).transpose(1, 2) for b in range(B)]
+        return torch.cat(parts, dim=0).transpose(1, 2)
     s_loc = S // P
     send = o.transpose(1, 2).reshape(P, s_loc, hp, D)
     if not send.is_contiguous():
@@ -116,9 +122,10 @@ def all_to_all_4D(input_: torch.Tensor, scatter_idx: int, gather_idx: int) -> to
     P = SP_STATE.sp_size
     if scatter_idx == 1 and gather_idx == 2:
         B, H, s_loc, D = input_.shape
-        x = input_.transpose(1, 2).reshape(1, s_loc, H, D) if B == 1 else None
-        if x is None:
-            raise ValueError("sequence-parallel attention supports batch size 1 per call")
+        if B != 1:       # utils.py:15-93 handles any batch: one sample after the other
+            parts = [all_to_all_4D(input_[b:b + 1], 1, 2).transpose(1, 2) for b in range(B)]
+            return torch.cat(parts, dim=0).transpose(1, 2)
+        x = input_.transpose(1, 2).reshape(1, s_loc, H, D)
         send = pack_heads(x.contiguous(), P)[0]                       # (P, S_loc, hp, D)
         recv = torch.empty_like(send)
         _a2a(recv, send)
