@@ -10,7 +10,9 @@ allocation per geometry) and
             token (``vb_attn_args.out_peer_ptrs``), already in the (S_loc, H, 128) layout the output projection reads.
 
 Two device-side barriers per layer order the remote stores against their consumers (see ``PeerExchange``).  Used for
-the top-1 (Eval) processors without a text segment; everything else takes the NCCL path in ``utils.py``.
+the top-1 (Eval) processors at batch size 1, Wan and HunyuanVideo (whose replicated text rows are filled locally on the
+way in and stored to every rank on the way out); the blended (Train) processors and larger batches take the NCCL path
+in ``utils.py``.
 """
 from __future__ import annotations
 
