@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges cost a few ns unless a profiler is attached
@@ -409,6 +411,7 @@ int vb_plan_create(vb_plan** out, const vb_plan_desc* desc) {
   pl->tile_window.assign(static_cast<size_t>(pl->n_tiles) * 6, 0);
   {
     std::vector<std::vector<int>> members;
+    std::map<std::array<int, 6>, int> index_of;             // window -> group
     const bool group_windows = getenv("VB_ATTN_NO_WINDOW_GROUPS") == nullptr;     // A/B switch: one group per tile
     for (int a = 0; a < pl->nt[0]; ++a)
       for (int b = 0; b < pl->nt[1]; ++b)
@@ -419,17 +422,19 @@ int vb_plan_create(vb_plan** out, const vb_plan_desc* desc) {
           window_range(a, pl->nt[0], d.window[0], lo, hi); w[0] = lo; w[3] = hi;
           window_range(b, pl->nt[1], d.window[1], lo, hi); w[1] = lo; w[4] = hi;
           window_range(c, pl->nt[2], d.window[2], lo, hi); w[2] = lo; w[5] = hi;
-          int found = -1;
-          for (size_t g = 0; group_windows && g < pl->groups.size() && found < 0; ++g)
-            if (memcmp(pl->groups[g].lo, w, 3 * sizeof(int)) == 0 && memcmp(pl->groups[g].hi, w + 3, 3 * sizeof(int)) == 0)
-              found = static_cast<int>(g);
-          if (found < 0) {
+          const std::array<int, 6> key = {w[0], w[1], w[2], w[3], w[4], w[5]};
+          auto hit = group_windows ? index_of.find(key) : index_of.end();
+          int found;
+          if (hit != index_of.end()) {
+            found = hit->second;
+          } else {
             vb_plan::WindowGroup g;
             for (int i = 0; i < 3; ++i) { g.lo[i] = w[i]; g.hi[i] = w[3 + i]; }
             g.row0 = 0; g.n_tiles = 0;
             found = static_cast<int>(pl->groups.size());
             pl->groups.push_back(g);
             members.emplace_back();
+            if (group_windows) index_of.emplace(key, found);
           }
           members[found].push_back(tile_id);
         }
